@@ -1,0 +1,113 @@
+/* medt_axial.h -- C ABI of libmedt_b200.so: the gated axial-attention hot path of
+ * Medical-Transformer as hand-written sm_100a CUDA.
+ *
+ * This is the drop-in boundary.  Every entry point replaces a piece of
+ * the reference's pure-PyTorch path in /root/reference/lib/models/axialnet.py:
+ *
+ *   mt_axial_forward   <- AxialAttention_dynamic.forward  axialnet.py:142-189  (variant 0)
+ *                         AxialAttention.forward          axialnet.py:52-92    (variant 1)
+ *                         AxialAttention_wopos.forward    axialnet.py:222-253  (variant 2)
+ *   mt_axial_backward  <- torch.autograd over the same lines (the reference has no
+ *                         hand-written backward; train.py:160 calls loss.backward())
+ *
+ * Conventions
+ *   - plain C, no torch types; all pointers are DEVICE pointers unless named host_*;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *     synchronises the device, never allocates, and is CUDA-graph capturable;
+ *   - the caller owns every buffer (activations, `saved`, `workspace`); sizes come from
+ *     the mt_*_bytes() queries;
+ *   - return value: 0 = ok, nonzero = error (message via mt_last_error(), thread-local);
+ *     nothing throws across the ABI, nothing calls exit();
+ *   - re-entrant: the device is whatever is current on the calling thread (torch's device
+ *     guard), so nn.DataParallel's one-thread-per-GPU model works.
+ *   - all tensors fp32, activations NCHW (the reference's layout and dtype).
+ */
+#ifndef MEDT_AXIAL_H_
+#define MEDT_AXIAL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MT_ABI_VERSION 1
+
+enum MtStatus {
+  MT_OK = 0,
+  MT_ERR_BAD_ARG = 1,      /* null pointer, non-positive size, stride not in {1,2,...}    */
+  MT_ERR_UNSUPPORTED = 2,  /* channel / length combination the kernels do not cover       */
+  MT_ERR_CUDA = 3          /* a CUDA runtime call failed (launch error, bad stream, ...)  */
+};
+
+enum MtVariant {
+  MT_VARIANT_GATED = 0,    /* AxialAttention_dynamic: rel-pos terms + 4 gates             */
+  MT_VARIANT_POS = 1,      /* AxialAttention: rel-pos terms, gates == 1                   */
+  MT_VARIANT_NOPOS = 2     /* AxialAttention_wopos: qk only, BN2d(G), BN1d(C)             */
+};
+
+/* Geometry of one axial-attention op.  groups is fixed at 8 (axialnet.py:400,715-728). */
+typedef struct MtAxialDesc {
+  int32_t N, C, H, W;      /* input x is N x C x H x W                                    */
+  int32_t axis;            /* 0: attend along H (reference width=False); 1: along W       */
+  int32_t stride;          /* AvgPool2d(stride) on the op's output (axialnet.py:186-187)  */
+  int32_t variant;         /* enum MtVariant                                              */
+  int32_t training;        /* 1: batch statistics + running-stat EMA; 0: running stats    */
+  int32_t ngroups;         /* statistic groups: N is split into `ngroups` consecutive
+                              blocks with SEPARATE batch statistics and one sequential EMA
+                              update each (16 = the batched LoGo patches); 1 = reference  */
+  float eps, momentum;     /* BatchNorm eps / momentum (1e-5 / 0.1 in the reference)      */
+} MtAxialDesc;
+
+/* Parameters and BN buffers of one AxialAttention* module (same tensors as its
+ * state_dict: qkv_transform.weight, relative, f_*, bn_qkv.*, bn_similarity.*, bn_output.*). */
+typedef struct MtAxialParams {
+  const float* w_qkv;      /* (2C, C)   qkv_transform.weight[:, :, 0]                     */
+  const float* relative;   /* (2*C/8, 2L-1) or NULL for MT_VARIANT_NOPOS                  */
+  const float* f_qr;       /* 0-dim gate tensors (device); NULL unless MT_VARIANT_GATED   */
+  const float* f_kr;
+  const float* f_sv;
+  const float* f_sve;
+  const float* bn_qkv_w;   const float* bn_qkv_b;   float* bn_qkv_rm;   float* bn_qkv_rv;   /* (2C)      */
+  const float* bn_sim_w;   const float* bn_sim_b;   float* bn_sim_rm;   float* bn_sim_rv;   /* (24) / (8) */
+  const float* bn_out_w;   const float* bn_out_b;   float* bn_out_rm;   float* bn_out_rv;   /* (2C) / (C) */
+} MtAxialParams;
+
+/* Gradients written by mt_axial_backward (each buffer fully overwritten; NULL = skip). */
+typedef struct MtAxialGrads {
+  float* dx;               /* (N, C, H, W)                                                */
+  float* dw_qkv;           /* (2C, C)                                                     */
+  float* drelative;        /* (2*C/8, 2L-1)                                               */
+  float* dgates;           /* (4): f_qr, f_kr, f_sv, f_sve                                */
+  float* dbn_qkv_w;        float* dbn_qkv_b;
+  float* dbn_sim_w;        float* dbn_sim_b;
+  float* dbn_out_w;        float* dbn_out_b;
+} MtAxialGrads;
+
+int mt_version(void);
+const char* mt_last_error(void);
+
+/* Bytes of the `saved` buffer (forward -> backward state: projection, un-normalised
+ * outputs, log-sum-exp, fp64 statistic accumulators) and of the backward workspace. */
+size_t mt_axial_saved_bytes(const MtAxialDesc* d);
+size_t mt_axial_bwd_workspace_bytes(const MtAxialDesc* d);
+
+/* out: (N, C, H/stride, W/stride).  Updates the running statistics in `p` when
+ * d->training (num_batches_tracked is the caller's: += ngroups). */
+int mt_axial_forward(const MtAxialDesc* d, const MtAxialParams* p, const float* x, float* out,
+                     void* saved, void* stream);
+
+/* dout: (N, C, H/stride, W/stride).  `saved` is what mt_axial_forward filled for the same
+ * desc / x / params. */
+int mt_axial_backward(const MtAxialDesc* d, const MtAxialParams* p, const float* x, const float* dout,
+                      const void* saved, void* workspace, const MtAxialGrads* g, void* stream);
+
+/* Number of kernels the last forward / backward call on this thread launched (used by
+ * bench.py's gpu_launches accounting). */
+int mt_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEDT_AXIAL_H_ */
