@@ -1,0 +1,640 @@
+// axial_bwd.cu -- backward of one axial-attention op.  The reference has no hand-written
+// backward (train.py:160 -> torch.autograd over axialnet.py:142-189); the closed forms
+// here are the ones pinned in oracle/axial_np.py::axial_backward against the reference.
+//
+// Every BatchNorm backward is the per-channel affine map  dx = A*dy + Bc + Cc*x  whose
+// coefficients need two grid-wide sums (sum dy, sum dy*x), hence four kernels:
+//   k_bwd_gather    dout (NCHW, through AvgPool) -> strips g_s ; sums for bn_output
+//   k_bwd_simstats  T[t,g] = sum dZ * S_t   (softmax + bn_similarity backward need it)
+//   k_bwd_attn      dq, dk, dv (w.r.t. normalised qkv), d relative ; sums for bn_qkv
+//   k_bwd_proj      bn_qkv backward, dX = W^T dY, dW = dY X^T, and all BN / gate parameter grads
+// P and dZ are recomputed from q,k,v and the saved log-sum-exp; no L x L tensor is stored.
+#include "common.cuh"
+
+__device__ __forceinline__ float gate_of_b(const float* p) { return p ? __ldg(p) : 1.f; }
+
+// ============================================================================ k_bwd_gather
+__global__ void __launch_bounds__(256)
+k_bwd_gather(Dims m, const float* __restrict__ dout, const float* __restrict__ oraw, float* __restrict__ gs,
+             double* __restrict__ bstats) {
+  __shared__ float red[3][8];
+  const int n = blockIdx.x / m.C, c = blockIdx.x - n * m.C;
+  const int grp = n / (m.N / m.ngroups);
+  const int NO = m.no, L = m.L, st_ = m.stride, Ho = m.H / st_, Wo = m.W / st_;
+  const float inv = 1.f / (float)(st_ * st_);
+  float s1 = 0.f, s2a = 0.f, s2b = 0.f;
+  for (int idx = threadIdx.x; idx < m.H * m.W; idx += blockDim.x) {
+    const int h = idx / m.W, w = idx - h * m.W;
+    const float g = __ldg(dout + ((size_t)blockIdx.x * Ho + h / st_) * Wo + w / st_) * inv;
+    const int b = m.axis == 0 ? n * m.W + w : n * m.H + h;
+    const int l = m.axis == 0 ? h : w;
+    gs[((size_t)b * m.C + c) * L + l] = g;
+    const float* o = oraw + ((size_t)b * NO * m.C + c * NO) * L + l;
+    s1 += g;
+    s2a = fmaf(g, __ldg(o), s2a);
+    if (NO == 2) s2b = fmaf(g, __ldg(o + L), s2b);
+  }
+  s1 = seg_sum(s1, 32); s2a = seg_sum(s2a, 32); s2b = seg_sum(s2b, 32);
+  const int wid = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { red[0][wid] = s1; red[1][wid] = s2a; red[2][wid] = s2b; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += red[threadIdx.x][k];
+    double* bs = bstats + (size_t)grp * m.nstat_b;
+    if (threadIdx.x == 0) atomicAdd(bs + m.b_out_s1 + c, (double)t);
+    else if (threadIdx.x == 1) atomicAdd(bs + m.b_out_s2 + c * NO, (double)t);
+    else if (NO == 2) atomicAdd(bs + m.b_out_s2 + c * NO + 1, (double)t);
+  }
+}
+
+// ============================================================================ shared loaders
+struct BwdSmem {
+  float *ca, *cb, *wsim, *sA, *sB, *sC, *oA, *oB, *oC, *red, *Yn, *R, *dOs, *Dl, *lses;
+};
+
+__device__ __forceinline__ BwdSmem carve(const Dims& m, float* sm, int SPB, int nred) {
+  BwdSmem s;
+  const int C = m.C, NOC = m.no * m.C;
+  s.ca = sm; s.cb = s.ca + 2 * C;
+  s.wsim = s.cb + 2 * C; s.sA = s.wsim + 24; s.sB = s.sA + 24; s.sC = s.sB + 24;
+  s.oA = s.sC + 24; s.oB = s.oA + NOC; s.oC = s.oB + NOC;
+  s.red = s.oC + NOC;
+  s.Yn = s.red + nred;
+  s.R = s.Yn + (size_t)SPB * 2 * C * m.LP;
+  s.dOs = s.R + (m.pos ? 2 * m.gp * (2 * m.L - 1) : 0);
+  s.Dl = s.dOs + (size_t)SPB * NOC * m.LP;
+  s.lses = s.Dl + (size_t)SPB * MT_G * m.L;
+  return s;
+}
+static size_t bwd_smem_floats(const Dims& m, int SPB, int nred) {
+  const size_t NOC = (size_t)m.no * m.C;
+  return 4 * (size_t)m.C + 96 + 3 * NOC + nred + (size_t)SPB * 2 * m.C * m.LP +
+         (m.pos ? 2 * (size_t)m.gp * (2 * m.L - 1) : 0) + (size_t)SPB * NOC * m.LP + 2 * (size_t)SPB * MT_G * m.L;
+}
+
+// Loads everything the attention backward needs for strips [b0, b0+SPB):
+//   normalised q,k,v ; relative ; dO (grad w.r.t. raw sv / sve, i.e. after bn_output backward
+//   and the gates) ; D_i = sum_c dO . O ; log-sum-exp ; softmax weights.
+__device__ __forceinline__ void bwd_load(const Dims& m, const MtAxialParams& p, const BwdSmem& s, int b0, int SPB,
+                                         int grp, const double* __restrict__ stats, const double* __restrict__ bstats,
+                                         const float* __restrict__ yraw, const float* __restrict__ oraw,
+                                         const float* __restrict__ lse, const float* __restrict__ gs,
+                                         bool need_sim_bwd) {
+  const int C = m.C, L = m.L, LP = m.LP, NO = m.no, NOC = NO * C;
+  const double* st = stats + (size_t)grp * m.nstat_f;
+  const double* bs = bstats + (size_t)grp * m.nstat_b;
+  {
+    const double n = (double)m.Bg * L;
+    for (int ch = threadIdx.x; ch < 2 * C; ch += blockDim.x) {
+      BnCoef c = bn_coef(m.training, m.training ? st[m.f_qkv_sum + ch] : 0.0, m.training ? st[m.f_qkv_sq + ch] : 0.0, n,
+                         1.f, p.bn_qkv_w[ch], p.bn_qkv_b[ch], p.bn_qkv_rm[ch], p.bn_qkv_rv[ch], m.eps);
+      s.ca[ch] = c.a; s.cb[ch] = c.b;
+    }
+    for (int ch = threadIdx.x; ch < NOC; ch += blockDim.x) {
+      const float f = (NO == 2 && (ch & 1)) ? gate_of_b(p.f_sve) : gate_of_b(p.f_sv);
+      BnBwdCoef k = bn_bwd_coef(m.training, m.training ? st[m.f_out_sum + ch] : 0.0,
+                                m.training ? st[m.f_out_sq + ch] : 0.0, n, f, p.bn_out_w[ch], p.bn_out_rv[ch], m.eps,
+                                m.training ? bs[m.b_out_s1 + ch / NO] : 0.0, m.training ? bs[m.b_out_s2 + ch] : 0.0);
+      s.oA[ch] = k.A; s.oB[ch] = k.Bc; s.oC[ch] = k.Cc;
+    }
+  }
+  if (threadIdx.x < m.nt * MT_G) {
+    const int t = threadIdx.x / MT_G, ch = threadIdx.x;
+    const float f = t == 0 ? 1.f : (t == 1 ? gate_of_b(p.f_qr) : gate_of_b(p.f_kr));
+    const double n = (double)m.Bg * L * L;
+    const double sum = m.training ? st[m.f_sim_sum + ch] : 0.0, sq = m.training ? st[m.f_sim_sq + ch] : 0.0;
+    BnCoef c = bn_coef(m.training, sum, sq, n, f, p.bn_sim_w[ch], p.bn_sim_b[ch], p.bn_sim_rm[ch], p.bn_sim_rv[ch], m.eps);
+    s.wsim[ch] = c.a * MT_LOG2E;
+    if (need_sim_bwd) {
+      // dy = dZ for every term; sum dZ == 0 exactly (softmax rows), so s1 = 0, s2 = T
+      BnBwdCoef k = bn_bwd_coef(m.training, sum, sq, n, f, p.bn_sim_w[ch], p.bn_sim_rv[ch], m.eps, 0.0,
+                                m.training ? bs[m.b_sim_t + ch] : 0.0);
+      s.sA[ch] = k.A; s.sB[ch] = k.Bc; s.sC[ch] = k.Cc;
+    }
+  }
+  if (m.pos) {
+    const int nrel = 2 * m.gp * (2 * L - 1);
+    for (int idx = threadIdx.x; idx < nrel; idx += blockDim.x) s.R[idx] = __ldg(p.relative + idx);
+  }
+  __syncthreads();
+  {
+    const int per = 2 * C * L;
+    const float* src = yraw + (size_t)b0 * per;
+    for (int idx = threadIdx.x; idx < SPB * per; idx += blockDim.x) {
+      int ss = idx / per, rem = idx - ss * per;
+      int ch = rem / L, l = rem - ch * L;
+      s.Yn[((size_t)ss * 2 * C + ch) * LP + l] = fmaf(s.ca[ch], __ldg(src + idx), s.cb[ch]);
+    }
+  }
+  {
+    const int per = NOC * L;
+    const float* src = oraw + (size_t)b0 * per;
+    for (int idx = threadIdx.x; idx < SPB * per; idx += blockDim.x) {
+      int ss = idx / per, rem = idx - ss * per;
+      int ch = rem / L, l = rem - ch * L;
+      float g = __ldg(gs + ((size_t)(b0 + ss) * C + ch / NO) * L + l);
+      s.dOs[((size_t)ss * NOC + ch) * LP + l] = fmaf(s.oA[ch], g, fmaf(s.oC[ch], __ldg(src + idx), s.oB[ch]));
+    }
+    for (int idx = threadIdx.x; idx < SPB * MT_G * L; idx += blockDim.x)
+      s.lses[idx] = __ldg(lse + (size_t)b0 * MT_G * L + idx);
+  }
+  __syncthreads();
+  {  // D[s][g][i] = sum over the head's output channels of dO * O_raw
+    const int per = NOC * L, gpn = m.gp * NO;
+    for (int idx = threadIdx.x; idx < SPB * MT_G * L; idx += blockDim.x) {
+      const int i = idx % L, g = (idx / L) % MT_G, ss = idx / (L * MT_G);
+      const float* o = oraw + (size_t)(b0 + ss) * per + (size_t)g * gpn * L + i;
+      const float* dO = s.dOs + ((size_t)ss * NOC + g * gpn) * LP + i;
+      float acc = 0.f;
+      for (int k = 0; k < gpn; ++k) acc = fmaf(dO[(size_t)k * LP], __ldg(o + (size_t)k * L), acc);
+      s.Dl[idx] = acc;
+    }
+  }
+  __syncthreads();
+}
+
+// One (i, j) pair of head `g` of strip `s`: raw similarities, P, dZ.
+template <int D, bool POS>
+struct PairEval {
+  float sqk, sqr, skr, P, dZ;
+  __device__ __forceinline__ void run(const float* __restrict__ Yb, const float* __restrict__ R,
+                                      const float* __restrict__ dOb, int LP, int L, int i, int j, float wqk,
+                                      float wqr, float wkr, float lse_i, float D_i) {
+    constexpr int GP = 2 * D;
+    const int RL = 2 * L - 1, mi = i - j + L - 1, mj = j - i + L - 1;
+    sqk = 0.f; sqr = 0.f; skr = 0.f;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      const float qc = Yb[c * LP + i], kc = Yb[(D + c) * LP + j];
+      sqk = fmaf(qc, kc, sqk);
+      if (POS) {
+        sqr = fmaf(qc, R[c * RL + mi], sqr);
+        skr = fmaf(kc, R[(D + c) * RL + mj], skr);
+      }
+    }
+    float z = wqk * sqk;
+    if (POS) z = fmaf(wqr, sqr, fmaf(wkr, skr, z));
+    P = ex2(z - lse_i);
+    float dP = 0.f;
+#pragma unroll
+    for (int c = 0; c < GP; ++c) {
+      if (POS) {
+        dP = fmaf(dOb[(2 * c) * LP + i], Yb[(GP + c) * LP + j], dP);
+        dP = fmaf(dOb[(2 * c + 1) * LP + i], R[(GP + c) * RL + mi], dP);
+      } else {
+        dP = fmaf(dOb[c * LP + i], Yb[(GP + c) * LP + j], dP);
+      }
+    }
+    dZ = P * (dP - D_i);
+  }
+};
+
+// ============================================================================ k_bwd_simstats
+template <int D, bool POS>
+__global__ void __launch_bounds__(256)
+k_bwd_simstats(Dims m, MtAxialParams p, const double* __restrict__ stats, double* __restrict__ bstats,
+               const float* __restrict__ yraw, const float* __restrict__ oraw, const float* __restrict__ lse,
+               const float* __restrict__ gs, int SPB, int segw) {
+  constexpr int GP = 2 * D;
+  extern __shared__ float sm[];
+  const int C = m.C, L = m.L, LP = m.LP, NO = m.no, NOC = NO * C;
+  const int b0 = blockIdx.x * SPB, grp = b0 / m.Bg;
+  BwdSmem s = carve(m, sm, SPB, 24);
+  if (threadIdx.x < 24) s.red[threadIdx.x] = 0.f;
+  bwd_load(m, p, s, b0, SPB, grp, stats, bstats, yraw, oraw, lse, gs, false);
+  const int nitems = SPB * MT_G * L;
+  for (int base = 0; base < nitems; base += blockDim.x) {
+    const int item = base + threadIdx.x;
+    const bool act = item < nitems;
+    const int it = act ? item : 0;
+    const int i = it % L, g = (it / L) % MT_G, ss = it / (L * MT_G);
+    const float* Yb = s.Yn + ((size_t)ss * 2 * C + g * 2 * GP) * LP;
+    const float* dOb = s.dOs + ((size_t)ss * NOC + g * GP * NO) * LP;
+    const float wqk = s.wsim[g], wqr = POS ? s.wsim[MT_G + g] : 0.f, wkr = POS ? s.wsim[2 * MT_G + g] : 0.f;
+    const float lse_i = s.lses[(ss * MT_G + g) * L + i], D_i = s.Dl[(ss * MT_G + g) * L + i];
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    PairEval<D, POS> pe;
+    for (int j = 0; j < L; ++j) {
+      pe.run(Yb, s.R, dOb, LP, L, i, j, wqk, wqr, wkr, lse_i, D_i);
+      t0 = fmaf(pe.dZ, pe.sqk, t0);
+      if (POS) { t1 = fmaf(pe.dZ, pe.sqr, t1); t2 = fmaf(pe.dZ, pe.skr, t2); }
+    }
+    if (!act) { t0 = t1 = t2 = 0.f; }
+    t0 = seg_sum(t0, segw);
+    if (POS) { t1 = seg_sum(t1, segw); t2 = seg_sum(t2, segw); }
+    if (act && (threadIdx.x & (segw - 1)) == 0) {
+      atomicAdd(s.red + g, t0);
+      if (POS) { atomicAdd(s.red + MT_G + g, t1); atomicAdd(s.red + 2 * MT_G + g, t2); }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < m.nt * MT_G)
+    atomicAdd(bstats + (size_t)grp * m.nstat_b + m.b_sim_t + threadIdx.x, (double)s.red[threadIdx.x]);
+}
+
+// ============================================================================ k_bwd_attn
+template <int D, bool POS>
+__global__ void __launch_bounds__(256)
+k_bwd_attn(Dims m, MtAxialParams p, const double* __restrict__ stats, double* __restrict__ bstats,
+           const float* __restrict__ yraw, const float* __restrict__ oraw, const float* __restrict__ lse,
+           const float* __restrict__ gs, float* __restrict__ dyh, float* __restrict__ drel, int SPB, int segw) {
+  constexpr int GP = 2 * D;
+  extern __shared__ float sm[];
+  const int C = m.C, L = m.L, LP = m.LP, NO = m.no, NOC = NO * C, RL = 2 * L - 1;
+  const int b0 = blockIdx.x * SPB, grp = b0 / m.Bg;
+  const int nrel = POS ? 2 * GP * RL : 0;
+  BwdSmem s = carve(m, sm, SPB, 4 * C + nrel);      // red: [2C][2] qkv sums, then dR accumulators
+  float* dRs = s.red + 4 * C;
+  for (int k = threadIdx.x; k < 4 * C + nrel; k += blockDim.x) s.red[k] = 0.f;
+  bwd_load(m, p, s, b0, SPB, grp, stats, bstats, yraw, oraw, lse, gs, true);
+  const int nitems = SPB * MT_G * L;
+
+  // ---- rows: dq[c,i] = sum_j dS_qk k[c,j] + dS_qr Rq[c,i-j]
+  for (int base = 0; base < nitems; base += blockDim.x) {
+    const int item = base + threadIdx.x;
+    const bool act = item < nitems;
+    const int it = act ? item : 0;
+    const int i = it % L, g = (it / L) % MT_G, ss = it / (L * MT_G);
+    const float* Yb = s.Yn + ((size_t)ss * 2 * C + g * 2 * GP) * LP;
+    const float* dOb = s.dOs + ((size_t)ss * NOC + g * GP * NO) * LP;
+    const float wqk = s.wsim[g], wqr = POS ? s.wsim[MT_G + g] : 0.f, wkr = POS ? s.wsim[2 * MT_G + g] : 0.f;
+    const float Aqk = s.sA[g], Bqk = s.sB[g], Cqk = s.sC[g];
+    const float Aqr = POS ? s.sA[MT_G + g] : 0.f, Bqr = POS ? s.sB[MT_G + g] : 0.f, Cqr = POS ? s.sC[MT_G + g] : 0.f;
+    const float lse_i = s.lses[(ss * MT_G + g) * L + i], D_i = s.Dl[(ss * MT_G + g) * L + i];
+    float dq[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) dq[c] = 0.f;
+    PairEval<D, POS> pe;
+    for (int j = 0; j < L; ++j) {
+      pe.run(Yb, s.R, dOb, LP, L, i, j, wqk, wqr, wkr, lse_i, D_i);
+      const float dSqk = fmaf(Aqk, pe.dZ, fmaf(Cqk, pe.sqk, Bqk));
+      const float dSqr = POS ? fmaf(Aqr, pe.dZ, fmaf(Cqr, pe.sqr, Bqr)) : 0.f;
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        dq[c] = fmaf(dSqk, Yb[(D + c) * LP + j], dq[c]);
+        if (POS) dq[c] = fmaf(dSqr, s.R[c * RL + (i - j + L - 1)], dq[c]);
+      }
+    }
+    const int b = b0 + ss;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      const int ch = g * 2 * GP + c;
+      float v = act ? dq[c] : 0.f;
+      float yr = act ? __ldg(yraw + ((size_t)b * 2 * C + ch) * L + i) : 0.f;
+      if (act) dyh[((size_t)b * 2 * C + ch) * L + i] = v;
+      float s1 = seg_sum(v, segw), s2 = seg_sum(v * yr, segw);
+      if (act && (threadIdx.x & (segw - 1)) == 0) { atomicAdd(s.red + ch * 2, s1); atomicAdd(s.red + ch * 2 + 1, s2); }
+    }
+  }
+
+  // ---- columns: dk[c,j] = sum_i dS_qk q[c,i] + dS_kr Rk[c,j-i] ; dv[c,j] = sum_i P dO_sv[c,i]
+  for (int base = 0; base < nitems; base += blockDim.x) {
+    const int item = base + threadIdx.x;
+    const bool act = item < nitems;
+    const int it = act ? item : 0;
+    const int j = it % L, g = (it / L) % MT_G, ss = it / (L * MT_G);
+    const float* Yb = s.Yn + ((size_t)ss * 2 * C + g * 2 * GP) * LP;
+    const float* dOb = s.dOs + ((size_t)ss * NOC + g * GP * NO) * LP;
+    const float wqk = s.wsim[g], wqr = POS ? s.wsim[MT_G + g] : 0.f, wkr = POS ? s.wsim[2 * MT_G + g] : 0.f;
+    const float Aqk = s.sA[g], Bqk = s.sB[g], Cqk = s.sC[g];
+    const float Akr = POS ? s.sA[2 * MT_G + g] : 0.f, Bkr = POS ? s.sB[2 * MT_G + g] : 0.f,
+                Ckr = POS ? s.sC[2 * MT_G + g] : 0.f;
+    const float* lsp = s.lses + (ss * MT_G + g) * L;
+    const float* Dp = s.Dl + (ss * MT_G + g) * L;
+    float dk[D], dv[GP];
+#pragma unroll
+    for (int c = 0; c < D; ++c) dk[c] = 0.f;
+#pragma unroll
+    for (int c = 0; c < GP; ++c) dv[c] = 0.f;
+    PairEval<D, POS> pe;
+    for (int i = 0; i < L; ++i) {
+      pe.run(Yb, s.R, dOb, LP, L, i, j, wqk, wqr, wkr, lsp[i], Dp[i]);
+      const float dSqk = fmaf(Aqk, pe.dZ, fmaf(Cqk, pe.sqk, Bqk));
+      const float dSkr = POS ? fmaf(Akr, pe.dZ, fmaf(Ckr, pe.skr, Bkr)) : 0.f;
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        dk[c] = fmaf(dSqk, Yb[c * LP + i], dk[c]);
+        if (POS) dk[c] = fmaf(dSkr, s.R[(D + c) * RL + (j - i + L - 1)], dk[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < GP; ++c) dv[c] = fmaf(pe.P, dOb[(c * NO) * LP + i], dv[c]);
+    }
+    const int b = b0 + ss;
+#pragma unroll
+    for (int c = 0; c < D + GP; ++c) {
+      const int ch = g * 2 * GP + D + c;             // k rows [D,2D), v rows [2D,4D) are contiguous
+      float v = act ? (c < D ? dk[c < D ? c : 0] : dv[c >= D ? c - D : 0]) : 0.f;
+      float yr = act ? __ldg(yraw + ((size_t)b * 2 * C + ch) * L + j) : 0.f;
+      if (act) dyh[((size_t)b * 2 * C + ch) * L + j] = v;
+      float s1 = seg_sum(v, segw), s2 = seg_sum(v * yr, segw);
+      if (act && (threadIdx.x & (segw - 1)) == 0) { atomicAdd(s.red + ch * 2, s1); atomicAdd(s.red + ch * 2 + 1, s2); }
+    }
+  }
+
+  // ---- diagonals: thread (s, g, mm) walks the pairs (i, j = i - mm + L - 1)
+  //      dRq[c,mm] += dS_qr q[c,i] ; dRv[c,mm] += P dO_sve[c,i] ; dRk[c, 2(L-1)-mm] += dS_kr k[c,j]
+  if (POS) {
+    const int nd = SPB * MT_G * RL;
+    for (int base = 0; base < nd; base += blockDim.x) {
+      const int item = base + threadIdx.x;
+      if (item < nd) {
+        const int mm = item % RL, g = (item / RL) % MT_G, ss = item / (RL * MT_G);
+        const float* Yb = s.Yn + ((size_t)ss * 2 * C + g * 2 * GP) * LP;
+        const float* dOb = s.dOs + ((size_t)ss * NOC + g * GP * NO) * LP;
+        const float wqk = s.wsim[g], wqr = s.wsim[MT_G + g], wkr = s.wsim[2 * MT_G + g];
+        const float Aqr = s.sA[MT_G + g], Bqr = s.sB[MT_G + g], Cqr = s.sC[MT_G + g];
+        const float Akr = s.sA[2 * MT_G + g], Bkr = s.sB[2 * MT_G + g], Ckr = s.sC[2 * MT_G + g];
+        const float* lsp = s.lses + (ss * MT_G + g) * L;
+        const float* Dp = s.Dl + (ss * MT_G + g) * L;
+        float aq[D], ak[D], av[GP];
+#pragma unroll
+        for (int c = 0; c < D; ++c) { aq[c] = 0.f; ak[c] = 0.f; }
+#pragma unroll
+        for (int c = 0; c < GP; ++c) av[c] = 0.f;
+        const int ilo = mm - (L - 1) > 0 ? mm - (L - 1) : 0, ihi = mm < L - 1 ? mm : L - 1;
+        PairEval<D, POS> pe;
+        for (int i = ilo; i <= ihi; ++i) {
+          const int j = i - mm + L - 1;
+          pe.run(Yb, s.R, dOb, LP, L, i, j, wqk, wqr, wkr, lsp[i], Dp[i]);
+          const float dSqr = fmaf(Aqr, pe.dZ, fmaf(Cqr, pe.sqr, Bqr));
+          const float dSkr = fmaf(Akr, pe.dZ, fmaf(Ckr, pe.skr, Bkr));
+#pragma unroll
+          for (int c = 0; c < D; ++c) {
+            aq[c] = fmaf(dSqr, Yb[c * LP + i], aq[c]);
+            ak[c] = fmaf(dSkr, Yb[(D + c) * LP + j], ak[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < GP; ++c) av[c] = fmaf(pe.P, dOb[(2 * c + 1) * LP + i], av[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          atomicAdd(dRs + c * RL + mm, aq[c]);
+          atomicAdd(dRs + (D + c) * RL + (2 * (L - 1) - mm), ak[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < GP; ++c) atomicAdd(dRs + (GP + c) * RL + mm, av[c]);
+      }
+    }
+  }
+  __syncthreads();
+  double* bs = bstats + (size_t)grp * m.nstat_b;
+  for (int ch = threadIdx.x; ch < 2 * C; ch += blockDim.x) {
+    atomicAdd(bs + m.b_qkv_s1 + ch, (double)s.red[ch * 2]);
+    atomicAdd(bs + m.b_qkv_s2 + ch, (double)s.red[ch * 2 + 1]);
+  }
+  if (POS)
+    for (int k = threadIdx.x; k < nrel; k += blockDim.x) atomicAdd(drel + k, dRs[k]);
+}
+
+// ============================================================================ k_bwd_proj
+// bn_qkv backward (dy_raw = A*dyh + Bc + Cc*y_raw), then dX = W^T dy_raw (this CTA's 16
+// input channels) and dW += dy_raw X^T (this CTA's 32 output channels) over a 64-position
+// tile.  CTA (0,0) additionally emits every BN-parameter and gate gradient from the fp64 sums.
+__global__ void __launch_bounds__(256)
+k_bwd_proj(Dims m, MtAxialParams p, MtAxialGrads gr, const float* __restrict__ x, const double* __restrict__ stats,
+           const double* __restrict__ bstats, const float* __restrict__ yraw, const float* __restrict__ dyh, int TS,
+           int TL, int tiles_per_group, int nTL) {
+  extern __shared__ float sm[];
+  const int C = m.C, tid = threadIdx.x;
+  float* qA = sm; float* qB = qA + 2 * C; float* qC = qB + 2 * C;
+  float* DYs = qC + 2 * C;                 // [2C][64]
+  float* Xs = DYs + 2 * C * 64;            // [C][65]
+  float* Ts = Xs + C * 65;                 // [16][64]
+  const int tile = blockIdx.x, grp = tile / tiles_per_group, tin = tile - grp * tiles_per_group;
+  const int ts_idx = tin / nTL, tl_idx = tin - ts_idx * nTL;
+  const int sb0 = ts_idx * TS, l0 = tl_idx * TL, npos = TS * TL;
+  const double* st = stats + (size_t)grp * m.nstat_f;
+  const double* bs = bstats + (size_t)grp * m.nstat_b;
+  for (int ch = tid; ch < 2 * C; ch += 256) {
+    BnBwdCoef k = bn_bwd_coef(m.training, m.training ? st[m.f_qkv_sum + ch] : 0.0, m.training ? st[m.f_qkv_sq + ch] : 0.0,
+                              (double)m.Bg * m.L, 1.f, p.bn_qkv_w[ch], p.bn_qkv_rv[ch], m.eps,
+                              m.training ? bs[m.b_qkv_s1 + ch] : 0.0, m.training ? bs[m.b_qkv_s2 + ch] : 0.0);
+    qA[ch] = k.A; qB[ch] = k.Bc; qC[ch] = k.Cc;
+  }
+  __syncthreads();
+  // dy_raw tile, strip order (l fastest): contiguous TL-runs of dyh / y_raw
+  for (int idx = tid; idx < 2 * C * 64; idx += 256) {
+    const int ch = idx >> 6, r = idx & 63;
+    const int s = r / TL, l = r - s * TL;
+    float v = 0.f;
+    if (r < npos && sb0 + s < m.Bg && l0 + l < m.L) {
+      const size_t a = ((size_t)(grp * m.Bg + sb0 + s) * 2 * C + ch) * m.L + l0 + l;
+      v = fmaf(qA[ch], __ldg(dyh + a), fmaf(qC[ch], __ldg(yraw + a), qB[ch]));
+    }
+    DYs[idx] = v;
+  }
+  for (int idx = tid; idx < C * 64; idx += 256) {
+    const int c = idx >> 6, r = idx & 63;
+    int s, l;
+    if (m.axis == 0) { s = r % TS; l = r / TS; } else { l = r % TL; s = r / TL; }
+    float v = 0.f;
+    const bool ok = r < npos && sb0 + s < m.Bg && l0 + l < m.L;
+    if (ok) v = __ldg(x + nchw_addr(m, grp * m.Bg + sb0 + s, c, l0 + l));
+    if (r < npos) Xs[c * 65 + s * TL + l] = v;
+  }
+  // unused tail positions of Xs (r >= npos) must read as zero in the dW dot products
+  for (int idx = tid; idx < C * 64; idx += 256) {
+    const int c = idx >> 6, r = idx & 63;
+    if (r >= npos) Xs[c * 65 + r] = 0.f;
+  }
+  __syncthreads();
+  // ---- dW for output channels [oc0, oc0+32)
+  const int oc0 = blockIdx.y * 32;
+  if (gr.dw_qkv) {
+    for (int k = tid; k < 32 * C; k += 256) {
+      const int ocl = k / C, c = k - ocl * C;
+      const float* dy = DYs + (oc0 + ocl) * 64;
+      const float* xr = Xs + c * 65;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int q = 0; q < 64; ++q) acc = fmaf(dy[q], xr[q], acc);
+      atomicAdd(gr.dw_qkv + (size_t)(oc0 + ocl) * C + c, acc);
+    }
+  }
+  // ---- dX for input channels [c0, c0+16)
+  if (gr.dx) {
+    const int c0 = blockIdx.y * 16;
+    const int pos = tid & 63, cl = tid >> 6;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int oc = 0; oc < 2 * C; ++oc) {
+      const float dy = DYs[oc * 64 + pos];
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(p.w_qkv + (size_t)oc * C + c0 + cl * 4));
+      a0 = fmaf(wv.x, dy, a0); a1 = fmaf(wv.y, dy, a1); a2 = fmaf(wv.z, dy, a2); a3 = fmaf(wv.w, dy, a3);
+    }
+    Ts[(cl * 4 + 0) * 64 + pos] = a0; Ts[(cl * 4 + 1) * 64 + pos] = a1;
+    Ts[(cl * 4 + 2) * 64 + pos] = a2; Ts[(cl * 4 + 3) * 64 + pos] = a3;
+    __syncthreads();
+    for (int idx = tid; idx < 16 * 64; idx += 256) {
+      const int cc = idx >> 6, r = idx & 63;
+      if (r >= npos) continue;
+      int s, l;
+      if (m.axis == 0) { s = r % TS; l = r / TS; } else { l = r % TL; s = r / TL; }
+      if (sb0 + s < m.Bg && l0 + l < m.L)
+        gr.dx[nchw_addr(m, grp * m.Bg + sb0 + s, c0 + cc, l0 + l)] = Ts[cc * 64 + s * TL + l];
+    }
+  }
+  // ---- parameter gradients from the accumulated sums (one CTA)
+  if (blockIdx.x == 0 && blockIdx.y == 0) {
+    const int NO = m.no, NOC = NO * C, NT = m.nt;
+    // bn_qkv
+    for (int ch = tid; ch < 2 * C; ch += 256) {
+      double dg = 0.0, db = 0.0;
+      for (int g = 0; g < m.ngroups; ++g) {
+        const double* st_ = stats + (size_t)g * m.nstat_f;
+        const double* bs_ = bstats + (size_t)g * m.nstat_b;
+        const double n = (double)m.Bg * m.L, s1 = bs_[m.b_qkv_s1 + ch], s2 = bs_[m.b_qkv_s2 + ch];
+        if (m.training) {
+          double mu = st_[m.f_qkv_sum + ch] / n, var = st_[m.f_qkv_sq + ch] / n - mu * mu;
+          if (var < 0.0) var = 0.0;
+          dg += (s2 - mu * s1) / sqrt(var + (double)m.eps);
+        } else {
+          dg += (s2 - (double)p.bn_qkv_rm[ch] * s1) / sqrt((double)p.bn_qkv_rv[ch] + (double)m.eps);
+        }
+        db += s1;
+      }
+      if (gr.dbn_qkv_w) gr.dbn_qkv_w[ch] = (float)dg;
+      if (gr.dbn_qkv_b) gr.dbn_qkv_b[ch] = (float)db;
+    }
+    // bn_output (+ gates f_sv, f_sve) and bn_similarity (+ gates f_qr, f_kr): per-channel terms into smem
+    double gpart[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int ch = tid; ch < NOC; ch += 256) {
+      const int sidx = NO == 2 ? (ch & 1) : 0;
+      const float f = sidx ? gate_of_b(p.f_sve) : gate_of_b(p.f_sv);
+      const double gam = p.bn_out_w[ch];
+      double dg = 0.0, db = 0.0;
+      for (int g = 0; g < m.ngroups; ++g) {
+        const double* st_ = stats + (size_t)g * m.nstat_f;
+        const double* bs_ = bstats + (size_t)g * m.nstat_b;
+        const double n = (double)m.Bg * m.L, s1 = bs_[m.b_out_s1 + ch / NO], s2 = bs_[m.b_out_s2 + ch];
+        if (m.training) {
+          double mu = st_[m.f_out_sum + ch] / n, var = st_[m.f_out_sq + ch] / n - mu * mu;
+          if (var < 0.0) var = 0.0;
+          const double su2 = (double)f * f * var + (double)m.eps, su = sqrt(su2);
+          dg += (double)f * (s2 - mu * s1) / su;
+          gpart[2 + sidx] += gam * (s2 - mu * s1) * (double)m.eps / (su2 * su);
+        } else {
+          const double inv = 1.0 / sqrt((double)p.bn_out_rv[ch] + (double)m.eps);
+          dg += ((double)f * s2 - (double)p.bn_out_rm[ch] * s1) * inv;
+          gpart[2 + sidx] += gam * inv * s2;
+        }
+        db += s1;
+      }
+      if (gr.dbn_out_w) gr.dbn_out_w[ch] = (float)dg;
+      if (gr.dbn_out_b) gr.dbn_out_b[ch] = (float)db;
+    }
+    if (tid < NT * MT_G) {
+      const int ch = tid, t = ch / MT_G;
+      const float f = t == 0 ? 1.f : (t == 1 ? gate_of_b(p.f_qr) : gate_of_b(p.f_kr));
+      const double gam = p.bn_sim_w[ch];
+      double dg = 0.0;
+      for (int g = 0; g < m.ngroups; ++g) {
+        const double* st_ = stats + (size_t)g * m.nstat_f;
+        const double* bs_ = bstats + (size_t)g * m.nstat_b;
+        const double n = (double)m.Bg * m.L * m.L, T = bs_[m.b_sim_t + ch];
+        if (m.training) {
+          double mu = st_[m.f_sim_sum + ch] / n, var = st_[m.f_sim_sq + ch] / n - mu * mu;
+          if (var < 0.0) var = 0.0;
+          const double su2 = (double)f * f * var + (double)m.eps, su = sqrt(su2);
+          dg += (double)f * T / su;
+          if (t > 0) gpart[t - 1] += gam * T * (double)m.eps / (su2 * su);
+        } else {
+          const double inv = 1.0 / sqrt((double)p.bn_sim_rv[ch] + (double)m.eps);
+          dg += (double)f * T * inv;
+          if (t > 0) gpart[t - 1] += gam * inv * T;
+        }
+      }
+      if (gr.dbn_sim_w) gr.dbn_sim_w[ch] = (float)dg;
+      if (gr.dbn_sim_b) gr.dbn_sim_b[ch] = 0.f;      // sum dZ == 0: softmax is shift invariant
+    }
+    // block-reduce the four gate partials (fixed order -> deterministic)
+    __shared__ double gred[4][256];
+    for (int k = 0; k < 4; ++k) gred[k][tid] = gpart[k];
+    __syncthreads();
+    if (tid < 4 && gr.dgates) {
+      double t = 0.0;
+      for (int k = 0; k < 256; ++k) t += gred[tid][k];
+      gr.dgates[tid] = (float)t;
+    }
+  }
+}
+
+// ============================================================================ host launcher
+static int pow2_le(int x) { int p = 1; while (p * 2 <= x) p *= 2; return p; }
+
+template <typename K>
+static cudaError_t set_smem_b(K kern, size_t bytes) {
+  if (bytes > 48 * 1024) return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return cudaSuccess;
+}
+
+#define MT_DISPATCH_DB(m, CALL)                                                    \
+  switch ((m).d) {                                                                 \
+    case 1: if ((m).pos) { CALL(1, true); } else { CALL(1, false); } break;        \
+    case 2: if ((m).pos) { CALL(2, true); } else { CALL(2, false); } break;        \
+    case 4: if ((m).pos) { CALL(4, true); } else { CALL(4, false); } break;        \
+    case 8: if ((m).pos) { CALL(8, true); } else { CALL(8, false); } break;        \
+    default: return -2;                                                            \
+  }
+
+int axial_backward_launch(const Dims& m, const MtAxialParams& p, const float* x, const float* dout, const char* saved,
+                          char* ws, const MtAxialGrads& gr, cudaStream_t st, int* nlaunch) {
+  const double* stats = reinterpret_cast<const double*>(saved + m.sv_stats);
+  const float* yraw = reinterpret_cast<const float*>(saved + m.sv_yraw);
+  const float* oraw = reinterpret_cast<const float*>(saved + m.sv_oraw);
+  const float* lse = reinterpret_cast<const float*>(saved + m.sv_lse);
+  double* bstats = reinterpret_cast<double*>(ws + m.ws_bstats);
+  float* gs = reinterpret_cast<float*>(ws + m.ws_gs);
+  float* dyh = reinterpret_cast<float*>(ws + m.ws_dyh);
+  int nl = 0;
+  if (cudaMemsetAsync(bstats, 0, sizeof(double) * (size_t)m.ngroups * m.nstat_b, st) != cudaSuccess) return -1;
+  if (gr.dw_qkv && cudaMemsetAsync(gr.dw_qkv, 0, sizeof(float) * 2 * (size_t)m.C * m.C, st) != cudaSuccess) return -1;
+  if (m.pos && gr.drelative &&
+      cudaMemsetAsync(gr.drelative, 0, sizeof(float) * 2 * (size_t)m.gp * (2 * m.L - 1), st) != cudaSuccess)
+    return -1;
+  k_bwd_gather<<<m.N * m.C, 256, 0, st>>>(m, dout, oraw, gs, bstats);
+  ++nl;
+  int spb = 1;
+  while (spb * MT_G * m.L < 256 && spb * 2 <= m.Bg && m.Bg % (spb * 2) == 0) spb *= 2;
+  const bool p2 = (m.L & (m.L - 1)) == 0;
+  const int segw = p2 ? (m.L < 32 ? m.L : 32) : 1;
+  (void)pow2_le;
+  if (m.training) {
+    const size_t smem = bwd_smem_floats(m, spb, 24) * sizeof(float);
+    if (smem > 227 * 1024) return -2;
+#define CALL_BS(DD, PP)                                                                               \
+    if (set_smem_b(k_bwd_simstats<DD, PP>, smem) != cudaSuccess) return -1;                             \
+    k_bwd_simstats<DD, PP><<<m.B / spb, 256, smem, st>>>(m, p, stats, bstats, yraw, oraw, lse, gs, spb, segw)
+    MT_DISPATCH_DB(m, CALL_BS)
+#undef CALL_BS
+    ++nl;
+  }
+  {
+    const int nrel = m.pos ? 2 * m.gp * (2 * m.L - 1) : 0;
+    const size_t smem = bwd_smem_floats(m, spb, 4 * m.C + nrel) * sizeof(float);
+    if (smem > 227 * 1024) return -2;
+    // drelative may be NULL only for the nopos variant
+    if (m.pos && !gr.drelative) return -3;
+#define CALL_BA(DD, PP)                                                                               \
+    if (set_smem_b(k_bwd_attn<DD, PP>, smem) != cudaSuccess) return -1;                                 \
+    k_bwd_attn<DD, PP><<<m.B / spb, 256, smem, st>>>(m, p, stats, bstats, yraw, oraw, lse, gs, dyh,     \
+                                                     gr.drelative, spb, segw)
+    MT_DISPATCH_DB(m, CALL_BA)
+#undef CALL_BA
+    ++nl;
+  }
+  {
+    int TS, TL;
+    if (m.axis == 1) { TL = m.L < 64 ? m.L : 64; TS = 64 / TL; if (TS > m.Bg) TS = m.Bg; }
+    else { TS = m.Bg < 8 ? m.Bg : 8; TL = 64 / TS; if (TL > m.L) TL = m.L; }
+    if (TS < 1) TS = 1;
+    const int nTL = (m.L + TL - 1) / TL, nTS = (m.Bg + TS - 1) / TS;
+    dim3 grid(m.ngroups * nTS * nTL, 2 * m.C / 32);
+    const size_t smem = sizeof(float) * (6 * (size_t)m.C + 2 * (size_t)m.C * 64 + (size_t)m.C * 65 + 16 * 64);
+    if (set_smem_b(k_bwd_proj, smem) != cudaSuccess) return -1;
+    k_bwd_proj<<<grid, 256, smem, st>>>(m, p, gr, x, stats, bstats, yraw, dyh, TS, TL, nTS * nTL, nTL);
+    ++nl;
+  }
+  *nlaunch = nl;
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}

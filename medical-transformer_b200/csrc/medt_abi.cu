@@ -1,0 +1,85 @@
+// medt_abi.cu -- the extern "C" surface declared in include/medt_axial.h.
+// No torch types, no exceptions, no allocation, no device synchronisation.
+#include <stdio.h>
+#include <string.h>
+#include "common.cuh"
+
+int axial_forward_launch(const Dims& m, const MtAxialParams& p, const float* x, float* out, char* saved,
+                         cudaStream_t st, int* nlaunch);
+int axial_backward_launch(const Dims& m, const MtAxialParams& p, const float* x, const float* dout, const char* saved,
+                          char* ws, const MtAxialGrads& gr, cudaStream_t st, int* nlaunch);
+
+static thread_local char g_err[512] = "";
+static thread_local int g_launches = 0;
+
+static int fail(int code, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+static int fail_cuda(const char* where) {
+  cudaError_t e = cudaGetLastError();
+  snprintf(g_err, sizeof(g_err), "%s: CUDA error %d (%s)", where, (int)e, cudaGetErrorString(e));
+  return MT_ERR_CUDA;
+}
+
+static int check_common(const MtAxialDesc* d, const MtAxialParams* p, Dims& m) {
+  if (!d || !p) return fail(MT_ERR_BAD_ARG, "null descriptor or params");
+  if (!make_dims(d, m))
+    return fail(MT_ERR_BAD_ARG, "bad MtAxialDesc (need N,C,H,W>0; C % 16 == 0; H,W % stride == 0; N % ngroups == 0)");
+  if (m.d != 1 && m.d != 2 && m.d != 4 && m.d != 8)
+    return fail(MT_ERR_UNSUPPORTED, "C/16 must be 1, 2, 4 or 8 (C in {16,32,64,128})");
+  if (m.training && (double)m.Bg * m.L < 2.0)
+    return fail(MT_ERR_BAD_ARG, "training needs more than one value per channel (as torch BatchNorm)");
+  if (!p->w_qkv || !p->bn_qkv_w || !p->bn_qkv_b || !p->bn_qkv_rm || !p->bn_qkv_rv || !p->bn_sim_w || !p->bn_sim_b ||
+      !p->bn_sim_rm || !p->bn_sim_rv || !p->bn_out_w || !p->bn_out_b || !p->bn_out_rm || !p->bn_out_rv)
+    return fail(MT_ERR_BAD_ARG, "null parameter pointer");
+  if (m.pos && !p->relative) return fail(MT_ERR_BAD_ARG, "relative is required for the position variants");
+  return MT_OK;
+}
+
+extern "C" {
+
+int mt_version(void) { return MT_ABI_VERSION; }
+const char* mt_last_error(void) { return g_err; }
+int mt_last_launch_count(void) { return g_launches; }
+
+size_t mt_axial_saved_bytes(const MtAxialDesc* d) {
+  Dims m;
+  if (!d || !make_dims(d, m)) return 0;
+  return m.sv_bytes;
+}
+size_t mt_axial_bwd_workspace_bytes(const MtAxialDesc* d) {
+  Dims m;
+  if (!d || !make_dims(d, m)) return 0;
+  return m.ws_bytes;
+}
+
+int mt_axial_forward(const MtAxialDesc* d, const MtAxialParams* p, const float* x, float* out, void* saved,
+                     void* stream) {
+  Dims m;
+  int rc = check_common(d, p, m);
+  if (rc) return rc;
+  if (!x || !out || !saved) return fail(MT_ERR_BAD_ARG, "null x / out / saved");
+  g_launches = 0;
+  int r = axial_forward_launch(m, *p, x, out, static_cast<char*>(saved), static_cast<cudaStream_t>(stream), &g_launches);
+  if (r == -2) return fail(MT_ERR_UNSUPPORTED, "shape needs more shared memory than one CTA has (C*L too large)");
+  if (r != 0) return fail_cuda("mt_axial_forward");
+  return MT_OK;
+}
+
+int mt_axial_backward(const MtAxialDesc* d, const MtAxialParams* p, const float* x, const float* dout,
+                      const void* saved, void* workspace, const MtAxialGrads* g, void* stream) {
+  Dims m;
+  int rc = check_common(d, p, m);
+  if (rc) return rc;
+  if (!x || !dout || !saved || !workspace || !g) return fail(MT_ERR_BAD_ARG, "null x / dout / saved / workspace / grads");
+  g_launches = 0;
+  int r = axial_backward_launch(m, *p, x, dout, static_cast<const char*>(saved), static_cast<char*>(workspace), *g,
+                                static_cast<cudaStream_t>(stream), &g_launches);
+  if (r == -2) return fail(MT_ERR_UNSUPPORTED, "shape needs more shared memory than one CTA has (C*L too large)");
+  if (r == -3) return fail(MT_ERR_BAD_ARG, "drelative is required for the position variants");
+  if (r != 0) return fail_cuda("mt_axial_backward");
+  return MT_OK;
+}
+
+}  // extern "C"

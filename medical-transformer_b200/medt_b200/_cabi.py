@@ -1,0 +1,95 @@
+"""ctypes binding of include/medt_axial.h (the reference-side stub INTEGRATION.md shows).
+
+Struct layouts mirror the header field for field; test_abi.py checks that every symbol the
+header declares is exported and that sizeof() agrees."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_LOCK = threading.Lock()
+
+MT_VARIANT = {"gated": 0, "pos": 1, "nopos": 2}
+
+
+class MtAxialDesc(C.Structure):
+    _fields_ = [("N", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("axis", C.c_int32), ("stride", C.c_int32), ("variant", C.c_int32),
+                ("training", C.c_int32), ("ngroups", C.c_int32),
+                ("eps", C.c_float), ("momentum", C.c_float)]
+
+
+_PARAM_FIELDS = ["w_qkv", "relative", "f_qr", "f_kr", "f_sv", "f_sve",
+                 "bn_qkv_w", "bn_qkv_b", "bn_qkv_rm", "bn_qkv_rv",
+                 "bn_sim_w", "bn_sim_b", "bn_sim_rm", "bn_sim_rv",
+                 "bn_out_w", "bn_out_b", "bn_out_rm", "bn_out_rv"]
+_GRAD_FIELDS = ["dx", "dw_qkv", "drelative", "dgates", "dbn_qkv_w", "dbn_qkv_b",
+                "dbn_sim_w", "dbn_sim_b", "dbn_out_w", "dbn_out_b"]
+
+
+class MtAxialParams(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in _PARAM_FIELDS]
+
+
+class MtAxialGrads(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in _GRAD_FIELDS]
+
+
+EXPORTS = ["mt_version", "mt_last_error", "mt_last_launch_count", "mt_axial_saved_bytes",
+           "mt_axial_bwd_workspace_bytes", "mt_axial_forward", "mt_axial_backward"]
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libmedt_b200.so")
+
+
+def load_library():
+    """Load libmedt_b200.so (built in-tree by __graft_entry__.build() / csrc/Makefile).
+    Fails loudly: the product has no fallback path."""
+    global _LIB
+    with _LOCK:
+        if _LIB is not None:
+            return _LIB
+        path = lib_path()
+        if not os.path.exists(path):
+            raise RuntimeError(
+                f"medt_b200: {path} is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C medical-transformer_b200/csrc`). There is no CPU / eager fallback.")
+        lib = C.CDLL(path)
+        lib.mt_version.restype = C.c_int
+        lib.mt_last_error.restype = C.c_char_p
+        lib.mt_last_launch_count.restype = C.c_int
+        lib.mt_axial_saved_bytes.restype = C.c_size_t
+        lib.mt_axial_saved_bytes.argtypes = [C.POINTER(MtAxialDesc)]
+        lib.mt_axial_bwd_workspace_bytes.restype = C.c_size_t
+        lib.mt_axial_bwd_workspace_bytes.argtypes = [C.POINTER(MtAxialDesc)]
+        lib.mt_axial_forward.restype = C.c_int
+        lib.mt_axial_forward.argtypes = [C.POINTER(MtAxialDesc), C.POINTER(MtAxialParams), C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]
+        lib.mt_axial_backward.restype = C.c_int
+        lib.mt_axial_backward.argtypes = [C.POINTER(MtAxialDesc), C.POINTER(MtAxialParams), C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.POINTER(MtAxialGrads), C.c_void_p]
+        _LIB = lib
+        return lib
+
+
+def abi_version() -> int:
+    return int(load_library().mt_version())
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load_library().mt_last_error().decode(errors="replace")
+        kind = {1: ValueError, 2: NotImplementedError}.get(rc, RuntimeError)
+        raise kind(f"{what} failed (status {rc}): {msg}")
+
+
+# launch accounting for bench.py's gpu_launches
+LAUNCHES = {"kernels": 0}
+
+
+def count_launches():
+    LAUNCHES["kernels"] += int(load_library().mt_last_launch_count())

@@ -179,3 +179,26 @@ if __name__ == "__main__":
         make_model("axialunet_128", "axialunet", 128, 2)
         make_model("logo_128", "logo", 128, 2)
         make_model("MedT_256", "MedT", 256, 1, modes=("eval",), with_grads=False)
+
+
+def make_schema():
+    """state_dict schema + init checksums of the reference factories (drop-in contract)."""
+    import json
+    out = {}
+    for factory, S in (("gated", 128), ("axialunet", 128), ("MedT", 128), ("logo", 128), ("gated", 64), ("MedT", 256)):
+        torch.manual_seed(1234)
+        m = getattr(ref, factory)(img_size=S, imgchan=3)
+        sd = m.state_dict()
+        out[f"{factory}_{S}"] = {
+            "keys": [[k, list(v.shape), str(v.dtype)] for k, v in sd.items()],
+            "init_sum": {k: float(v.double().sum()) for k, v in sd.items() if v.dtype.is_floating_point},
+            "requires_grad_false": [k for k, p in m.named_parameters() if not p.requires_grad],
+            "trainable": int(sum(p.numel() for p in m.parameters() if p.requires_grad)),
+        }
+    with open(os.path.join(HERE, "schema.json"), "w") as f:
+        json.dump(out, f)
+    print("wrote schema")
+
+
+if __name__ == "__main__" and (not sys.argv[1:] or "schema" in sys.argv[1:]):
+    make_schema()
