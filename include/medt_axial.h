@@ -103,6 +103,17 @@ int mt_axial_forward(const MtAxialDesc* d, const MtAxialParams* p, const float* 
 int mt_axial_backward(const MtAxialDesc* d, const MtAxialParams* p, const float* x, const float* dout,
                       const void* saved, void* workspace, const MtAxialGrads* g, void* stream);
 
+/* Profiling hooks (bench.py roofline, ncu): launch only the stages selected by `stage_mask`
+ * of a forward (bit 0 k_proj, 1 k_sim_stats, 2 k_attn, 3 k_out) or backward (bit 0
+ * k_bwd_gather, 1 k_bwd_simstats, 2 k_bwd_attn, 3 k_bwd_proj) on buffers a full call has
+ * already filled.  Statistic accumulators are NOT re-zeroed, so outputs are meaningless;
+ * durations are those of the real launches.  Mask 15 == the full call minus the memsets. */
+int mt_axial_forward_stages(const MtAxialDesc* d, const MtAxialParams* p, const float* x, float* out,
+                            void* saved, void* stream, int stage_mask);
+int mt_axial_backward_stages(const MtAxialDesc* d, const MtAxialParams* p, const float* x, const float* dout,
+                             const void* saved, void* workspace, const MtAxialGrads* g, void* stream,
+                             int stage_mask);
+
 /* Number of kernels the last forward / backward call on this thread launched (used by
  * bench.py's gpu_launches accounting). */
 int mt_last_launch_count(void);

@@ -109,7 +109,7 @@ __device__ __forceinline__ void bwd_load(const Dims& m, const MtAxialParams& p, 
     if (need_sim_bwd) {
       // dy = dZ for every term; sum dZ == 0 exactly (softmax rows), so s1 = 0, s2 = T
       BnBwdCoef k = bn_bwd_coef(m.training, sum, sq, n, f, p.bn_sim_w[ch], p.bn_sim_rv[ch], m.eps, 0.0,
-                                m.training ? bs[m.b_sim_t + ch] : 0.0);
+                                bs[m.b_sim_t + ch]);
       s.sA[ch] = k.A; s.sB[ch] = k.Bc; s.sC[ch] = k.Cc;
     }
   }
@@ -578,7 +578,7 @@ static cudaError_t set_smem_b(K kern, size_t bytes) {
   }
 
 int axial_backward_launch(const Dims& m, const MtAxialParams& p, const float* x, const float* dout, const char* saved,
-                          char* ws, const MtAxialGrads& gr, cudaStream_t st, int* nlaunch) {
+                          char* ws, const MtAxialGrads& gr, cudaStream_t st, int* nlaunch, int mask) {
   const double* stats = reinterpret_cast<const double*>(saved + m.sv_stats);
   const float* yraw = reinterpret_cast<const float*>(saved + m.sv_yraw);
   const float* oraw = reinterpret_cast<const float*>(saved + m.sv_oraw);
@@ -587,19 +587,23 @@ int axial_backward_launch(const Dims& m, const MtAxialParams& p, const float* x,
   float* gs = reinterpret_cast<float*>(ws + m.ws_gs);
   float* dyh = reinterpret_cast<float*>(ws + m.ws_dyh);
   int nl = 0;
+  if (mask == 0x1f) {
   if (cudaMemsetAsync(bstats, 0, sizeof(double) * (size_t)m.ngroups * m.nstat_b, st) != cudaSuccess) return -1;
   if (gr.dw_qkv && cudaMemsetAsync(gr.dw_qkv, 0, sizeof(float) * 2 * (size_t)m.C * m.C, st) != cudaSuccess) return -1;
   if (m.pos && gr.drelative &&
       cudaMemsetAsync(gr.drelative, 0, sizeof(float) * 2 * (size_t)m.gp * (2 * m.L - 1), st) != cudaSuccess)
     return -1;
-  k_bwd_gather<<<m.N * m.C, 256, 0, st>>>(m, dout, oraw, gs, bstats);
-  ++nl;
+  }
+  if (mask & 1) {
+    k_bwd_gather<<<m.N * m.C, 256, 0, st>>>(m, dout, oraw, gs, bstats);
+    ++nl;
+  }
   int spb = 1;
   while (spb * MT_G * m.L < 256 && spb * 2 <= m.Bg && m.Bg % (spb * 2) == 0) spb *= 2;
   const bool p2 = (m.L & (m.L - 1)) == 0;
   const int segw = p2 ? (m.L < 32 ? m.L : 32) : 1;
   (void)pow2_le;
-  if (m.training) {
+  if (mask & 2) {  // T = sum dZ*S_t is needed in eval mode too (bn_similarity.weight and the gate gradients)
     const size_t smem = bwd_smem_floats(m, spb, 24) * sizeof(float);
     if (smem > 227 * 1024) return -2;
 #define CALL_BS(DD, PP)                                                                               \
@@ -609,7 +613,7 @@ int axial_backward_launch(const Dims& m, const MtAxialParams& p, const float* x,
 #undef CALL_BS
     ++nl;
   }
-  {
+  if (mask & 4) {
     const int nrel = m.pos ? 2 * m.gp * (2 * m.L - 1) : 0;
     const size_t smem = bwd_smem_floats(m, spb, 4 * m.C + nrel) * sizeof(float);
     if (smem > 227 * 1024) return -2;
@@ -623,7 +627,7 @@ int axial_backward_launch(const Dims& m, const MtAxialParams& p, const float* x,
 #undef CALL_BA
     ++nl;
   }
-  {
+  if (mask & 8) {
     int TS, TL;
     if (m.axis == 1) { TL = m.L < 64 ? m.L : 64; TS = 64 / TL; if (TS > m.Bg) TS = m.Bg; }
     else { TS = m.Bg < 8 ? m.Bg : 8; TL = 64 / TS; if (TL > m.L) TL = m.L; }

@@ -378,16 +378,16 @@ static cudaError_t set_smem(K kern, size_t bytes) {
 
 // returns 0 ok, -1 cuda error (cudaGetLastError holds it), -2 unsupported
 int axial_forward_launch(const Dims& m, const MtAxialParams& p, const float* x, float* out, char* saved,
-                         cudaStream_t st, int* nlaunch) {
+                         cudaStream_t st, int* nlaunch, int mask) {
   double* stats = reinterpret_cast<double*>(saved + m.sv_stats);
   float* yraw = reinterpret_cast<float*>(saved + m.sv_yraw);
   float* oraw = reinterpret_cast<float*>(saved + m.sv_oraw);
   float* lse = reinterpret_cast<float*>(saved + m.sv_lse);
   int nl = 0;
-  if (m.training) {
+  if (m.training && mask == 0x1f) {
     if (cudaMemsetAsync(stats, 0, sizeof(double) * (size_t)m.ngroups * m.nstat_f, st) != cudaSuccess) return -1;
   }
-  {  // k_proj
+  if (mask & 1) {  // k_proj
     int TS, TL;
     if (m.axis == 1) { TL = m.L < 64 ? m.L : 64; TS = 64 / TL; if (TS > m.Bg) TS = m.Bg; }
     else { TS = m.Bg < 8 ? m.Bg : 8; TL = 64 / TS; if (TL > m.L) TL = m.L; }
@@ -399,7 +399,7 @@ int axial_forward_launch(const Dims& m, const MtAxialParams& p, const float* x, 
     k_proj<<<grid, 256, smem, st>>>(m, x, p.w_qkv, yraw, stats, TS, TL, nTS * nTL, nTL);
     ++nl;
   }
-  if (m.training) {
+  if (m.training && (mask & 2)) {
     LaunchPlan pl = plan_attn(m, 0, 48);
     if (pl.smem_attn > 227 * 1024) return -2;
 #define CALL_SIM(DD, PP)                                                                       \
@@ -409,7 +409,7 @@ int axial_forward_launch(const Dims& m, const MtAxialParams& p, const float* x, 
 #undef CALL_SIM
     ++nl;
   }
-  {
+  if (mask & 4) {
     LaunchPlan pl = plan_attn(m, 0, 24 + 2 * m.no * m.C);
     if (pl.smem_attn > 227 * 1024) return -2;
 #define CALL_ATTN(DD, PP)                                                                      \
@@ -419,8 +419,10 @@ int axial_forward_launch(const Dims& m, const MtAxialParams& p, const float* x, 
 #undef CALL_ATTN
     ++nl;
   }
-  k_out<<<m.N * m.C, 256, 0, st>>>(m, p, stats, oraw, out);
-  ++nl;
+  if (mask & 8) {
+    k_out<<<m.N * m.C, 256, 0, st>>>(m, p, stats, oraw, out);
+    ++nl;
+  }
   *nlaunch = nl;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

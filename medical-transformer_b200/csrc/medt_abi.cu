@@ -5,9 +5,9 @@
 #include "common.cuh"
 
 int axial_forward_launch(const Dims& m, const MtAxialParams& p, const float* x, float* out, char* saved,
-                         cudaStream_t st, int* nlaunch);
+                         cudaStream_t st, int* nlaunch, int mask);
 int axial_backward_launch(const Dims& m, const MtAxialParams& p, const float* x, const float* dout, const char* saved,
-                          char* ws, const MtAxialGrads& gr, cudaStream_t st, int* nlaunch);
+                          char* ws, const MtAxialGrads& gr, cudaStream_t st, int* nlaunch, int mask);
 
 static thread_local char g_err[512] = "";
 static thread_local int g_launches = 0;
@@ -54,32 +54,49 @@ size_t mt_axial_bwd_workspace_bytes(const MtAxialDesc* d) {
   return m.ws_bytes;
 }
 
-int mt_axial_forward(const MtAxialDesc* d, const MtAxialParams* p, const float* x, float* out, void* saved,
-                     void* stream) {
+static int forward_impl(const MtAxialDesc* d, const MtAxialParams* p, const float* x, float* out, void* saved,
+                        void* stream, int mask) {
   Dims m;
   int rc = check_common(d, p, m);
   if (rc) return rc;
   if (!x || !out || !saved) return fail(MT_ERR_BAD_ARG, "null x / out / saved");
   g_launches = 0;
-  int r = axial_forward_launch(m, *p, x, out, static_cast<char*>(saved), static_cast<cudaStream_t>(stream), &g_launches);
+  int r = axial_forward_launch(m, *p, x, out, static_cast<char*>(saved), static_cast<cudaStream_t>(stream), &g_launches, mask);
   if (r == -2) return fail(MT_ERR_UNSUPPORTED, "shape needs more shared memory than one CTA has (C*L too large)");
   if (r != 0) return fail_cuda("mt_axial_forward");
   return MT_OK;
 }
+int mt_axial_forward(const MtAxialDesc* d, const MtAxialParams* p, const float* x, float* out, void* saved,
+                     void* stream) {
+  return forward_impl(d, p, x, out, saved, stream, 0x1f);
+}
+int mt_axial_forward_stages(const MtAxialDesc* d, const MtAxialParams* p, const float* x, float* out, void* saved,
+                            void* stream, int stage_mask) {
+  return forward_impl(d, p, x, out, saved, stream, stage_mask & 0xf);
+}
 
-int mt_axial_backward(const MtAxialDesc* d, const MtAxialParams* p, const float* x, const float* dout,
-                      const void* saved, void* workspace, const MtAxialGrads* g, void* stream) {
+static int backward_impl(const MtAxialDesc* d, const MtAxialParams* p, const float* x, const float* dout,
+                         const void* saved, void* workspace, const MtAxialGrads* g, void* stream, int mask) {
   Dims m;
   int rc = check_common(d, p, m);
   if (rc) return rc;
   if (!x || !dout || !saved || !workspace || !g) return fail(MT_ERR_BAD_ARG, "null x / dout / saved / workspace / grads");
   g_launches = 0;
   int r = axial_backward_launch(m, *p, x, dout, static_cast<const char*>(saved), static_cast<char*>(workspace), *g,
-                                static_cast<cudaStream_t>(stream), &g_launches);
+                                static_cast<cudaStream_t>(stream), &g_launches, mask);
   if (r == -2) return fail(MT_ERR_UNSUPPORTED, "shape needs more shared memory than one CTA has (C*L too large)");
   if (r == -3) return fail(MT_ERR_BAD_ARG, "drelative is required for the position variants");
   if (r != 0) return fail_cuda("mt_axial_backward");
   return MT_OK;
+}
+int mt_axial_backward(const MtAxialDesc* d, const MtAxialParams* p, const float* x, const float* dout,
+                      const void* saved, void* workspace, const MtAxialGrads* g, void* stream) {
+  return backward_impl(d, p, x, dout, saved, workspace, g, stream, 0x1f);
+}
+int mt_axial_backward_stages(const MtAxialDesc* d, const MtAxialParams* p, const float* x, const float* dout,
+                             const void* saved, void* workspace, const MtAxialGrads* g, void* stream,
+                             int stage_mask) {
+  return backward_impl(d, p, x, dout, saved, workspace, g, stream, stage_mask & 0xf);
 }
 
 }  // extern "C"

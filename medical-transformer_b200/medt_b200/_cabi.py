@@ -39,7 +39,8 @@ class MtAxialGrads(C.Structure):
 
 
 EXPORTS = ["mt_version", "mt_last_error", "mt_last_launch_count", "mt_axial_saved_bytes",
-           "mt_axial_bwd_workspace_bytes", "mt_axial_forward", "mt_axial_backward"]
+           "mt_axial_bwd_workspace_bytes", "mt_axial_forward", "mt_axial_backward",
+           "mt_axial_forward_stages", "mt_axial_backward_stages"]
 
 
 def lib_path() -> str:
@@ -72,6 +73,10 @@ def load_library():
         lib.mt_axial_backward.restype = C.c_int
         lib.mt_axial_backward.argtypes = [C.POINTER(MtAxialDesc), C.POINTER(MtAxialParams), C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.POINTER(MtAxialGrads), C.c_void_p]
+        lib.mt_axial_forward_stages.restype = C.c_int
+        lib.mt_axial_forward_stages.argtypes = lib.mt_axial_forward.argtypes + [C.c_int]
+        lib.mt_axial_backward_stages.restype = C.c_int
+        lib.mt_axial_backward_stages.argtypes = lib.mt_axial_backward.argtypes + [C.c_int]
         _LIB = lib
         return lib
 

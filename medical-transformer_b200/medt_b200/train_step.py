@@ -1,0 +1,157 @@
+"""The user-facing training step of the B200 path.
+
+`TrainStep(model)` is what replaces the body of the reference's inner loop
+(train.py:134-162: H2D copy, forward, cross-entropy, backward, Adam) for one process per GPU:
+
+  * the whole step -- forward, loss, backward, gradient all-reduce, Adam -- is captured ONCE in
+    a CUDA graph and replayed (the 128-px step is launch-bound: ~500 kernels of a few us);
+  * data parallelism is one process per GPU with a SINGLE flat fp32 gradient bucket
+    all-reduced (AVG) by NCCL over NVLink/NVSwitch inside the graph -- the B200 equivalent of
+    the reference's nn.DataParallel(device_ids=[0,1]) (train.py:104-108).  BatchNorm statistics
+    stay per rank (DataParallel semantics: no SyncBN in the reference);
+  * parameters that receive no gradient (frozen gates before train.py:169-171 flips them;
+    MedT's never-used adjust_p / AxialBlock_wopos.conv1) are left out of the bucket and of the
+    optimizer step exactly as torch.optim.Adam skips `grad is None` parameters; call
+    `recapture()` after changing requires_grad.
+
+`step(x_host, y_host)` is the end-to-end call: pinned-host -> device copies of the batch,
+graph replay, device -> pinned-host copy of the loss.  `step_resident()` replays on the
+batch already in HBM.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+
+class TrainStep:
+    def __init__(self, model, batch_shape, lr=1e-3, weight_decay=1e-5, device=None, use_graph=True,
+                 process_group=None, loss_slots=64):
+        self.model = model
+        self.device = torch.device(device if device is not None else next(model.parameters()).device)
+        if self.device.type != "cuda":
+            raise RuntimeError("medt_b200.TrainStep needs a CUDA device; there is no CPU path")
+        self.lr, self.weight_decay, self.use_graph = lr, weight_decay, use_graph
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        n, c, h, w = batch_shape
+        self.x = torch.zeros(batch_shape, device=self.device)
+        self.y = torch.zeros((n, h, w), dtype=torch.long, device=self.device)
+        self.x_pin = torch.zeros(batch_shape).pin_memory()
+        self.y_pin = torch.zeros((n, h, w), dtype=torch.long).pin_memory()
+        self.loss = torch.zeros((), device=self.device)
+        self.loss_pin = torch.zeros(loss_slots).pin_memory()
+        self._slot = 0
+        self.graph = None
+        self.opt = None
+        self.steps_done = 0
+        self._build()
+
+    # ------------------------------------------------------------------ setup
+    def _probe_active_params(self):
+        """Parameters that actually receive a gradient (one eager forward/backward)."""
+        for p in self.model.parameters():
+            p.grad = None
+        state = {k: v.clone() for k, v in self.model.state_dict().items()}       # keep BN buffers untouched
+        loss = F.cross_entropy(self.model(self.x), self.y)
+        loss.backward()
+        active = [p for p in self.model.parameters() if p.grad is not None]
+        self.model.load_state_dict(state)
+        for p in self.model.parameters():
+            p.grad = None
+        return active
+
+    def _build(self):
+        self.model.train()
+        self.active = self._probe_active_params()
+        total = sum(p.numel() for p in self.active)
+        self.flat_grad = torch.zeros(total, device=self.device)
+        off = 0
+        for p in self.active:                       # every .grad is a view into the single bucket
+            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        old_state = self.opt.state_dict() if self.opt is not None else None
+        self.opt = torch.optim.Adam(self.active, lr=self.lr, weight_decay=self.weight_decay, capturable=True,
+                                    foreach=True)
+        if old_state is not None and len(old_state["param_groups"][0]["params"]) == len(self.active):
+            self.opt.load_state_dict(old_state)
+        self.graph = None
+        if self.use_graph:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            state = {k: v.clone() for k, v in self.model.state_dict().items()}
+            opt_state = None
+            with torch.cuda.stream(side):           # warm-up (allocator, cuDNN autotune, lazy init)
+                for _ in range(3):
+                    self._step_body()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            # undo the warm-up's parameter / statistic / optimizer updates
+            self.model.load_state_dict(state)
+            self.opt = torch.optim.Adam(self.active, lr=self.lr, weight_decay=self.weight_decay, capturable=True,
+                                        foreach=True)
+            if old_state is not None and len(old_state["param_groups"][0]["params"]) == len(self.active):
+                self.opt.load_state_dict(old_state)
+            del opt_state
+            # one more eager step on the fresh optimizer so its state tensors exist before capture
+            self._step_body()
+            self.model.load_state_dict(state)
+            for st in self.opt.state.values():
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+            torch.cuda.synchronize(self.device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._step_body()
+            torch.cuda.synchronize(self.device)
+            # capture does not execute: state is still the restored one
+
+    def recapture(self):
+        """Call after flipping requires_grad (train.py:169-171) or changing lr."""
+        self._build()
+
+    def _step_body(self):
+        self.flat_grad.zero_()
+        out = self.model(self.x)
+        loss = F.cross_entropy(out, self.y)                    # LogNLLLoss == cross_entropy (metrics.py:17-20)
+        loss.backward()
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG, group=self.pg)
+        self.opt.step()
+        self.loss.copy_(loss.detach())
+
+    # ------------------------------------------------------------------ stepping
+    def step_resident(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step_body()
+        self.steps_done += 1
+        return self.loss
+
+    def step(self, x_host, y_host):
+        """End-to-end step from host tensors.  Returns the slot of `loss_pin` that will hold this
+        step's loss once the stream has drained (no host sync here)."""
+        if x_host.is_pinned():
+            self.x.copy_(x_host, non_blocking=True)
+        else:
+            self.x_pin.copy_(x_host)
+            self.x.copy_(self.x_pin, non_blocking=True)
+        if y_host.is_pinned():
+            self.y.copy_(y_host, non_blocking=True)
+        else:
+            self.y_pin.copy_(y_host)
+            self.y.copy_(self.y_pin, non_blocking=True)
+        self.step_resident()
+        slot = self._slot
+        self.loss_pin[slot:slot + 1].copy_(self.loss.reshape(1), non_blocking=True)
+        self._slot = (slot + 1) % self.loss_pin.numel()
+        return slot
+
+    def h2d_bytes_per_step(self):
+        return self.x.numel() * self.x.element_size() + self.y.numel() * self.y.element_size()
+
+    def d2h_bytes_per_step(self):
+        return self.loss.element_size()

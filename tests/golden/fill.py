@@ -17,7 +17,14 @@ def _rs(name: str, salt: int = 0) -> np.random.RandomState:
 
 
 def tensor_for(name: str, shape, salt: int = 0) -> np.ndarray:
-    """Value for the state_dict entry `name` (float64; caller casts)."""
+    """Value for the state_dict entry `name`: float64 array whose entries are exactly
+    representable in float32, so the fp64 reference run, the fp64 oracle and the fp32 CUDA
+    path all see bit-identical parameters."""
+    v = _tensor_for(name, shape, salt)
+    return v if v.dtype == np.int64 else v.astype(np.float32).astype(np.float64)
+
+
+def _tensor_for(name: str, shape, salt: int = 0) -> np.ndarray:
     rs = _rs(name, salt)
     shape = tuple(shape)
     leaf = name.split(".")[-1]
@@ -47,7 +54,7 @@ def tensor_for(name: str, shape, salt: int = 0) -> np.ndarray:
 def image_batch(n, c, s, salt=0) -> np.ndarray:
     """Synthetic images in [0,1) quantised to k/255 like to_tensor(uint8) (utils.py:92)."""
     rs = _rs("image_batch", salt)
-    return np.floor(rs.random_sample((n, c, s, s)) * 256.0) / 255.0
+    return (np.floor(rs.random_sample((n, c, s, s)) * 256.0) / 255.0).astype(np.float32).astype(np.float64)
 
 
 def mask_batch(n, s, salt=0) -> np.ndarray:

@@ -57,7 +57,7 @@ def _fill_module(mod, prefix, dtype, salt=0):
 
 
 def _rand(name, shape):
-    return np.random.RandomState((sum(map(ord, name)) * 2654435761) % (2 ** 31)).standard_normal(shape)
+    return np.random.RandomState((sum(map(ord, name)) * 2654435761) % (2 ** 31)).standard_normal(shape).astype(np.float32).astype(np.float64)
 
 
 def make_op(name, cls, C, N, H, W, width, stride, ngroups=1):

@@ -48,3 +48,26 @@ def rel_err(a, b):
     b = np.asarray(b, dtype=np.float64)
     den = np.linalg.norm(b)
     return float(np.linalg.norm(a - b) / den) if den > 0 else float(np.abs(a).max())
+
+
+def load_model_golden(tag):
+    return np.load(os.path.join(GOLDEN, f"model_{tag}.npz"))
+
+
+def build_filled_model(factory, S, dtype=None, device="cpu"):
+    """Drop-in model with the deterministic fill of tests/golden/fill.py (== what make_golden.py
+    loaded into the reference)."""
+    import torch
+    import lib
+    f = lib.models.axialunet if factory == "axialunet" else getattr(lib.models.axialnet, factory)
+    m = f(img_size=S, imgchan=3)
+    vals = fill.fill_state_dict(m.state_dict())
+    sd = m.state_dict()
+    with torch.no_grad():
+        for k, v in vals.items():
+            sd[k].copy_(torch.as_tensor(v).to(sd[k].dtype))
+    for p in m.parameters():
+        p.requires_grad_(True)
+    if dtype is not None:
+        m = m.to(dtype)          # fill values are fp32-representable, so this cast is exact
+    return m.to(device)

