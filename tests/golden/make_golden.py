@@ -138,6 +138,17 @@ def make_model(tag, factory, S, N, modes=("train", "eval"), with_grads=True):
                     lg = m(x)
                 loss = torch.nn.functional.cross_entropy(lg, y)
             logits[dtype] = lg.detach()
+            if with_grads:
+                gdict = {k: (torch.zeros_like(p) if p.grad is None else p.grad).double() for k, p in m.named_parameters()}
+                if dtype == torch.float64:
+                    g64 = gdict
+                else:   # the reference's OWN fp32-vs-fp64 gradient gap = the noise floor for the fp32 CUDA path
+                    tot = float(np.sqrt(sum(float(g.norm()) ** 2 for g in g64.values())))
+                    out[f"{mode}_ref_gradnorm_fp32_vs_fp64_worst"] = np.array(max(
+                        abs(float(gdict[k].norm()) - float(g64[k].norm())) / max(float(g64[k].norm()), 1e-3 * tot)
+                        for k in g64))
+                    out[f"{mode}_ref_grad_fp32_vs_fp64_worst"] = np.array(max(
+                        float((gdict[k] - g64[k]).norm()) / max(float(g64[k].norm()), 1e-3 * tot) for k in g64))
             if dtype == torch.float64:
                 out[f"{mode}_logits"] = lg.detach().numpy().astype(np.float32)
                 out[f"{mode}_loss"] = np.array(loss.item())
@@ -159,7 +170,8 @@ def make_model(tag, factory, S, N, modes=("train", "eval"), with_grads=True):
         a, b = logits[torch.float64], logits[torch.float32].double()
         out[f"{mode}_ref_fp32_vs_fp64_rel"] = np.array(((a - b).norm() / a.norm()).item())
         out[f"{mode}_ref_fp32_vs_fp64_maxabs"] = np.array((a - b).abs().max().item())
-        print(tag, mode, "loss", out[f"{mode}_loss"], "ref fp32-vs-fp64 rel", out[f"{mode}_ref_fp32_vs_fp64_rel"])
+        print(tag, mode, "loss", out[f"{mode}_loss"], "ref fp32-vs-fp64 rel", out[f"{mode}_ref_fp32_vs_fp64_rel"],
+              "grad gap", out.get(f"{mode}_ref_grad_fp32_vs_fp64_worst"), out.get(f"{mode}_ref_gradnorm_fp32_vs_fp64_worst"))
     np.savez_compressed(os.path.join(HERE, f"model_{tag}.npz"), **out)
     print("wrote model", tag)
 

@@ -87,6 +87,7 @@ def measure(tag, factory, S, N, mode):
 
 @pytest.mark.parametrize("tag,factory,S,N,modes", CASES)
 def test_model_matches_reference_golden(tag, factory, S, N, modes):
+    z = load_model_golden(tag)
     for mode in modes:
         r = measure(tag, factory, S, N, mode)
         msg = f"{tag}/{mode}: {r}"
@@ -94,8 +95,11 @@ def test_model_matches_reference_golden(tag, factory, S, N, modes):
         assert r["loss_abs"] < (2e-3 if mode == "train" else 1e-5), msg
         assert r["thr_mask_mismatch_safe"] == 0 and r["argmax_mismatch_safe"] == 0, msg
         if "gradnorm_worst_rel" in r:
-            assert r["gradnorm_worst_rel"] < (0.05 if mode == "train" else 5e-3), msg
-            assert r["select_grad_worst_rel"] < (0.05 if mode == "train" else 5e-3), msg
+            # gradient tolerance = 3x the reference's OWN fp32-vs-fp64 gradient gap on this case
+            # (train mode: 0.14-0.25 -- chaotic amplification through the stacked batch-stat BNs)
+            gap = float(z[f"{mode}_ref_grad_fp32_vs_fp64_worst"])
+            assert r["gradnorm_worst_rel"] < max(1e-4, 3 * gap), msg
+            assert r["select_grad_worst_rel"] < max(1e-4, 3 * gap), msg
         if "buffers_worst_rel" in r:
             assert r["buffers_worst_rel"] < 2e-3, msg
 
