@@ -126,7 +126,10 @@ def axial_attention(x, mod, ngroups: int = 1):
         bq.weight, bq.bias, bs.weight, bs.bias, bo.weight, bo.bias,
         bq.running_mean, bq.running_var, bs.running_mean, bs.running_var, bo.running_mean, bo.running_var, cfg)
     if training:
-        with torch.no_grad():
-            for bn in (bq, bs, bo):
-                bn.num_batches_tracked += ngroups
+        for bn in (bq, bs, bo):
+            if getattr(bn, "_nbt_deferred", False):      # TrainStep adds all counters in one launch
+                bn._stat_groups_bn = ngroups
+            else:
+                with torch.no_grad():
+                    bn.num_batches_tracked += ngroups
     return out

@@ -13,7 +13,10 @@ import torch.nn.functional as F
 
 def batch_norm_grouped(x, bn, groups: int = 1):
     if groups == 1 or not bn.training:
-        return bn(x)
+        if bn.training and not getattr(bn, "_nbt_deferred", False):
+            bn.num_batches_tracked += 1
+        return F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training,
+                            bn.momentum if bn.momentum is not None else 0.1, bn.eps)
     pn, c, h, w = x.shape
     n = pn // groups
     xg = x.view(groups, n, c, h, w)
@@ -28,5 +31,8 @@ def batch_norm_grouped(x, bn, groups: int = 1):
         keep = (1.0 - m) ** groups
         bn.running_mean.mul_(keep).add_((wts * mean.view(groups, c)).sum(0))
         bn.running_var.mul_(keep).add_((wts * var.view(groups, c) * (cnt / max(cnt - 1, 1))).sum(0))
-        bn.num_batches_tracked += groups
+        if getattr(bn, "_nbt_deferred", False):
+            bn._stat_groups_bn = groups
+        else:
+            bn.num_batches_tracked += groups
     return y.view(pn, c, h, w)

@@ -64,16 +64,26 @@ class TrainStep:
 
     def _build(self):
         self.model.train()
-        self.active = self._probe_active_params()
+        # every BatchNorm counter becomes a 0-dim view of ONE int64 tensor: one add per step
+        bns = [m for m in self.model.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)]
+        self._nbt = torch.stack([b.num_batches_tracked.to(self.device) for b in bns]) if bns else None
+        for i, b in enumerate(bns):
+            b.num_batches_tracked = self._nbt[i]
+            b._nbt_deferred = True
+        self.active = self._probe_active_params()          # its forward records each BN's statistic-group count
+        self._nbt_inc = torch.tensor([int(getattr(b, "_stat_groups_bn", 1)) for b in bns], device=self.device)
         total = sum(p.numel() for p in self.active)
-        self.flat_grad = torch.zeros(total, device=self.device)
-        off = 0
-        for p in self.active:                       # every .grad is a view into the single bucket
-            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        self.flat_grad = torch.zeros(total, device=self.device) if self.world > 1 else None
+        self._grad_views = None
+        if self.world > 1:
+            off, views = 0, []
+            for p in self.active:                   # views of the single all-reduce bucket
+                views.append(self.flat_grad[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            self._grad_views = views
         old_state = self.opt.state_dict() if self.opt is not None else None
         self.opt = torch.optim.Adam(self.active, lr=self.lr, weight_decay=self.weight_decay, capturable=True,
-                                    foreach=True)
+                                    fused=True)
         if old_state is not None and len(old_state["param_groups"][0]["params"]) == len(self.active):
             self.opt.load_state_dict(old_state)
         self.graph = None
@@ -81,7 +91,6 @@ class TrainStep:
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             state = {k: v.clone() for k, v in self.model.state_dict().items()}
-            opt_state = None
             with torch.cuda.stream(side):           # warm-up (allocator, cuDNN autotune, lazy init)
                 for _ in range(3):
                     self._step_body()
@@ -90,10 +99,9 @@ class TrainStep:
             # undo the warm-up's parameter / statistic / optimizer updates
             self.model.load_state_dict(state)
             self.opt = torch.optim.Adam(self.active, lr=self.lr, weight_decay=self.weight_decay, capturable=True,
-                                        foreach=True)
+                                        fused=True)
             if old_state is not None and len(old_state["param_groups"][0]["params"]) == len(self.active):
                 self.opt.load_state_dict(old_state)
-            del opt_state
             # one more eager step on the fresh optimizer so its state tensors exist before capture
             self._step_body()
             self.model.load_state_dict(state)
@@ -113,13 +121,19 @@ class TrainStep:
         self._build()
 
     def _step_body(self):
-        self.flat_grad.zero_()
+        for p in self.active:
+            p.grad = None
         out = self.model(self.x)
         loss = F.cross_entropy(out, self.y)                    # LogNLLLoss == cross_entropy (metrics.py:17-20)
         loss.backward()
         if self.world > 1:
+            torch.cat([p.grad.reshape(-1) for p in self.active], out=self.flat_grad)
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG, group=self.pg)
+            for p, v in zip(self.active, self._grad_views):
+                p.grad = v
         self.opt.step()
+        if self._nbt is not None:
+            self._nbt += self._nbt_inc
         self.loss.copy_(loss.detach())
 
     # ------------------------------------------------------------------ stepping

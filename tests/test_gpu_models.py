@@ -98,8 +98,8 @@ def test_model_matches_reference_golden(tag, factory, S, N, modes):
             # gradient tolerance = 3x the reference's OWN fp32-vs-fp64 gradient gap on this case
             # (train mode: 0.14-0.25 -- chaotic amplification through the stacked batch-stat BNs)
             gap = float(z[f"{mode}_ref_grad_fp32_vs_fp64_worst"])
-            assert r["gradnorm_worst_rel"] < max(1e-4, 3 * gap), msg
-            assert r["select_grad_worst_rel"] < max(1e-4, 3 * gap), msg
+            assert r["gradnorm_worst_rel"] < max(1e-3, 3 * gap), msg
+            assert r["select_grad_worst_rel"] < max(1e-3, 3 * gap), msg
         if "buffers_worst_rel" in r:
             assert r["buffers_worst_rel"] < 2e-3, msg
 
