@@ -13,41 +13,6 @@
 
 __device__ __forceinline__ float gate_of_b(const float* p) { return p ? __ldg(p) : 1.f; }
 
-// ============================================================================ k_bwd_gather
-__global__ void __launch_bounds__(256)
-k_bwd_gather(Dims m, const float* __restrict__ dout, const float* __restrict__ oraw, float* __restrict__ gs,
-             double* __restrict__ bstats) {
-  __shared__ float red[3][8];
-  const int n = blockIdx.x / m.C, c = blockIdx.x - n * m.C;
-  const int grp = n / (m.N / m.ngroups);
-  const int NO = m.no, L = m.L, st_ = m.stride, Ho = m.H / st_, Wo = m.W / st_;
-  const float inv = 1.f / (float)(st_ * st_);
-  float s1 = 0.f, s2a = 0.f, s2b = 0.f;
-  for (int idx = threadIdx.x; idx < m.H * m.W; idx += blockDim.x) {
-    const int h = idx / m.W, w = idx - h * m.W;
-    const float g = __ldg(dout + ((size_t)blockIdx.x * Ho + h / st_) * Wo + w / st_) * inv;
-    const int b = m.axis == 0 ? n * m.W + w : n * m.H + h;
-    const int l = m.axis == 0 ? h : w;
-    gs[((size_t)b * m.C + c) * L + l] = g;
-    const float* o = oraw + ((size_t)b * NO * m.C + c * NO) * L + l;
-    s1 += g;
-    s2a = fmaf(g, __ldg(o), s2a);
-    if (NO == 2) s2b = fmaf(g, __ldg(o + L), s2b);
-  }
-  s1 = seg_sum(s1, 32); s2a = seg_sum(s2a, 32); s2b = seg_sum(s2b, 32);
-  const int wid = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) == 0) { red[0][wid] = s1; red[1][wid] = s2a; red[2][wid] = s2b; }
-  __syncthreads();
-  if (threadIdx.x < 3) {
-    float t = 0.f;
-    for (int k = 0; k < 8; ++k) t += red[threadIdx.x][k];
-    double* bs = bstats + (size_t)grp * m.nstat_b;
-    if (threadIdx.x == 0) atomicAdd(bs + m.b_out_s1 + c, (double)t);
-    else if (threadIdx.x == 1) atomicAdd(bs + m.b_out_s2 + c * NO, (double)t);
-    else if (NO == 2) atomicAdd(bs + m.b_out_s2 + c * NO + 1, (double)t);
-  }
-}
-
 // ============================================================================ shared loaders
 struct BwdSmem {
   float *ca, *cb, *wsim, *sA, *sB, *sC, *oA, *oB, *oC, *red, *Yn, *R, *dOs, *Dl, *lses;
@@ -82,20 +47,20 @@ __device__ __forceinline__ void bwd_load(const Dims& m, const MtAxialParams& p, 
                                          const float* __restrict__ lse, const float* __restrict__ gs,
                                          bool need_sim_bwd) {
   const int C = m.C, L = m.L, LP = m.LP, NO = m.no, NOC = NO * C;
-  const double* st = stats + (size_t)grp * m.nstat_f;
-  const double* bs = bstats + (size_t)grp * m.nstat_b;
+#define ST(off) stat_get(m, stats, grp, m.nstat_f, (off))
+#define BS(off) stat_get(m, bstats, grp, m.nstat_b, (off))
   {
     const double n = (double)m.Bg * L;
     for (int ch = threadIdx.x; ch < 2 * C; ch += blockDim.x) {
-      BnCoef c = bn_coef(m.training, m.training ? st[m.f_qkv_sum + ch] : 0.0, m.training ? st[m.f_qkv_sq + ch] : 0.0, n,
+      BnCoef c = bn_coef(m.training, m.training ? ST(m.f_qkv_sum + ch) : 0.0, m.training ? ST(m.f_qkv_sq + ch) : 0.0, n,
                          1.f, p.bn_qkv_w[ch], p.bn_qkv_b[ch], p.bn_qkv_rm[ch], p.bn_qkv_rv[ch], m.eps);
       s.ca[ch] = c.a; s.cb[ch] = c.b;
     }
     for (int ch = threadIdx.x; ch < NOC; ch += blockDim.x) {
       const float f = (NO == 2 && (ch & 1)) ? gate_of_b(p.f_sve) : gate_of_b(p.f_sv);
-      BnBwdCoef k = bn_bwd_coef(m.training, m.training ? st[m.f_out_sum + ch] : 0.0,
-                                m.training ? st[m.f_out_sq + ch] : 0.0, n, f, p.bn_out_w[ch], p.bn_out_rv[ch], m.eps,
-                                m.training ? bs[m.b_out_s1 + ch / NO] : 0.0, m.training ? bs[m.b_out_s2 + ch] : 0.0);
+      BnBwdCoef k = bn_bwd_coef(m.training, m.training ? ST(m.f_out_sum + ch) : 0.0,
+                                m.training ? ST(m.f_out_sq + ch) : 0.0, n, f, p.bn_out_w[ch], p.bn_out_rv[ch], m.eps,
+                                m.training ? BS(m.b_out_s1 + ch / NO) : 0.0, m.training ? BS(m.b_out_s2 + ch) : 0.0);
       s.oA[ch] = k.A; s.oB[ch] = k.Bc; s.oC[ch] = k.Cc;
     }
   }
@@ -103,13 +68,15 @@ __device__ __forceinline__ void bwd_load(const Dims& m, const MtAxialParams& p, 
     const int t = threadIdx.x / MT_G, ch = threadIdx.x;
     const float f = t == 0 ? 1.f : (t == 1 ? gate_of_b(p.f_qr) : gate_of_b(p.f_kr));
     const double n = (double)m.Bg * L * L;
-    const double sum = m.training ? st[m.f_sim_sum + ch] : 0.0, sq = m.training ? st[m.f_sim_sq + ch] : 0.0;
+    const double sum = m.training ? ST(m.f_sim_sum + ch) : 0.0, sq = m.training ? ST(m.f_sim_sq + ch) : 0.0;
     BnCoef c = bn_coef(m.training, sum, sq, n, f, p.bn_sim_w[ch], p.bn_sim_b[ch], p.bn_sim_rm[ch], p.bn_sim_rv[ch], m.eps);
     s.wsim[ch] = c.a * MT_LOG2E;
     if (need_sim_bwd) {
       // dy = dZ for every term; sum dZ == 0 exactly (softmax rows), so s1 = 0, s2 = T
       BnBwdCoef k = bn_bwd_coef(m.training, sum, sq, n, f, p.bn_sim_w[ch], p.bn_sim_rv[ch], m.eps, 0.0,
-                                bs[m.b_sim_t + ch]);
+                                BS(m.b_sim_t + ch));
+#undef ST
+#undef BS
       s.sA[ch] = k.A; s.sB[ch] = k.Bc; s.sC[ch] = k.Cc;
     }
   }
@@ -230,7 +197,7 @@ k_bwd_simstats(Dims m, MtAxialParams p, const double* __restrict__ stats, double
   }
   __syncthreads();
   if (threadIdx.x < m.nt * MT_G)
-    atomicAdd(bstats + (size_t)grp * m.nstat_b + m.b_sim_t + threadIdx.x, (double)s.red[threadIdx.x]);
+    MT_GADD(m, stat_slot(m, bstats, grp, m.nstat_b, blockIdx.x) + m.b_sim_t + threadIdx.x, (double)s.red[threadIdx.x]);
 }
 
 // ============================================================================ k_bwd_attn
@@ -378,188 +345,20 @@ k_bwd_attn(Dims m, MtAxialParams p, const double* __restrict__ stats, double* __
     }
   }
   __syncthreads();
-  double* bs = bstats + (size_t)grp * m.nstat_b;
+  double* bs = stat_slot(m, bstats, grp, m.nstat_b, blockIdx.x);
   for (int ch = threadIdx.x; ch < 2 * C; ch += blockDim.x) {
-    atomicAdd(bs + m.b_qkv_s1 + ch, (double)s.red[ch * 2]);
-    atomicAdd(bs + m.b_qkv_s2 + ch, (double)s.red[ch * 2 + 1]);
+    MT_GADD(m, bs + m.b_qkv_s1 + ch, (double)s.red[ch * 2]);
+    MT_GADD(m, bs + m.b_qkv_s2 + ch, (double)s.red[ch * 2 + 1]);
   }
   if (POS)
-    for (int k = threadIdx.x; k < nrel; k += blockDim.x) atomicAdd(drel + k, dRs[k]);
-}
-
-// ============================================================================ k_bwd_proj
-// bn_qkv backward (dy_raw = A*dyh + Bc + Cc*y_raw), then dX = W^T dy_raw (this CTA's 16
-// input channels) and dW += dy_raw X^T (this CTA's 32 output channels) over a 64-position
-// tile.  CTA (0,0) additionally emits every BN-parameter and gate gradient from the fp64 sums.
-__global__ void __launch_bounds__(256)
-k_bwd_proj(Dims m, MtAxialParams p, MtAxialGrads gr, const float* __restrict__ x, const double* __restrict__ stats,
-           const double* __restrict__ bstats, const float* __restrict__ yraw, const float* __restrict__ dyh, int TS,
-           int TL, int tiles_per_group, int nTL) {
-  extern __shared__ float sm[];
-  const int C = m.C, tid = threadIdx.x;
-  float* qA = sm; float* qB = qA + 2 * C; float* qC = qB + 2 * C;
-  float* DYs = qC + 2 * C;                 // [2C][64]
-  float* Xs = DYs + 2 * C * 64;            // [C][65]
-  float* Ts = Xs + C * 65;                 // [16][64]
-  const int tile = blockIdx.x, grp = tile / tiles_per_group, tin = tile - grp * tiles_per_group;
-  const int ts_idx = tin / nTL, tl_idx = tin - ts_idx * nTL;
-  const int sb0 = ts_idx * TS, l0 = tl_idx * TL, npos = TS * TL;
-  const double* st = stats + (size_t)grp * m.nstat_f;
-  const double* bs = bstats + (size_t)grp * m.nstat_b;
-  for (int ch = tid; ch < 2 * C; ch += 256) {
-    BnBwdCoef k = bn_bwd_coef(m.training, m.training ? st[m.f_qkv_sum + ch] : 0.0, m.training ? st[m.f_qkv_sq + ch] : 0.0,
-                              (double)m.Bg * m.L, 1.f, p.bn_qkv_w[ch], p.bn_qkv_rv[ch], m.eps,
-                              m.training ? bs[m.b_qkv_s1 + ch] : 0.0, m.training ? bs[m.b_qkv_s2 + ch] : 0.0);
-    qA[ch] = k.A; qB[ch] = k.Bc; qC[ch] = k.Cc;
-  }
-  __syncthreads();
-  // dy_raw tile, strip order (l fastest): contiguous TL-runs of dyh / y_raw
-  for (int idx = tid; idx < 2 * C * 64; idx += 256) {
-    const int ch = idx >> 6, r = idx & 63;
-    const int s = r / TL, l = r - s * TL;
-    float v = 0.f;
-    if (r < npos && sb0 + s < m.Bg && l0 + l < m.L) {
-      const size_t a = ((size_t)(grp * m.Bg + sb0 + s) * 2 * C + ch) * m.L + l0 + l;
-      v = fmaf(qA[ch], __ldg(dyh + a), fmaf(qC[ch], __ldg(yraw + a), qB[ch]));
-    }
-    DYs[idx] = v;
-  }
-  for (int idx = tid; idx < C * 64; idx += 256) {
-    const int c = idx >> 6, r = idx & 63;
-    int s, l;
-    if (m.axis == 0) { s = r % TS; l = r / TS; } else { l = r % TL; s = r / TL; }
-    float v = 0.f;
-    const bool ok = r < npos && sb0 + s < m.Bg && l0 + l < m.L;
-    if (ok) v = __ldg(x + nchw_addr(m, grp * m.Bg + sb0 + s, c, l0 + l));
-    if (r < npos) Xs[c * 65 + s * TL + l] = v;
-  }
-  // unused tail positions of Xs (r >= npos) must read as zero in the dW dot products
-  for (int idx = tid; idx < C * 64; idx += 256) {
-    const int c = idx >> 6, r = idx & 63;
-    if (r >= npos) Xs[c * 65 + r] = 0.f;
-  }
-  __syncthreads();
-  // ---- dW for output channels [oc0, oc0+32)
-  const int oc0 = blockIdx.y * 32;
-  if (gr.dw_qkv) {
-    for (int k = tid; k < 32 * C; k += 256) {
-      const int ocl = k / C, c = k - ocl * C;
-      const float* dy = DYs + (oc0 + ocl) * 64;
-      const float* xr = Xs + c * 65;
-      float acc = 0.f;
-#pragma unroll 8
-      for (int q = 0; q < 64; ++q) acc = fmaf(dy[q], xr[q], acc);
-      atomicAdd(gr.dw_qkv + (size_t)(oc0 + ocl) * C + c, acc);
-    }
-  }
-  // ---- dX for input channels [c0, c0+16)
-  if (gr.dx) {
-    const int c0 = blockIdx.y * 16;
-    const int pos = tid & 63, cl = tid >> 6;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (int oc = 0; oc < 2 * C; ++oc) {
-      const float dy = DYs[oc * 64 + pos];
-      const float4 wv = __ldg(reinterpret_cast<const float4*>(p.w_qkv + (size_t)oc * C + c0 + cl * 4));
-      a0 = fmaf(wv.x, dy, a0); a1 = fmaf(wv.y, dy, a1); a2 = fmaf(wv.z, dy, a2); a3 = fmaf(wv.w, dy, a3);
-    }
-    Ts[(cl * 4 + 0) * 64 + pos] = a0; Ts[(cl * 4 + 1) * 64 + pos] = a1;
-    Ts[(cl * 4 + 2) * 64 + pos] = a2; Ts[(cl * 4 + 3) * 64 + pos] = a3;
-    __syncthreads();
-    for (int idx = tid; idx < 16 * 64; idx += 256) {
-      const int cc = idx >> 6, r = idx & 63;
-      if (r >= npos) continue;
-      int s, l;
-      if (m.axis == 0) { s = r % TS; l = r / TS; } else { l = r % TL; s = r / TL; }
-      if (sb0 + s < m.Bg && l0 + l < m.L)
-        gr.dx[nchw_addr(m, grp * m.Bg + sb0 + s, c0 + cc, l0 + l)] = Ts[cc * 64 + s * TL + l];
-    }
-  }
-  // ---- parameter gradients from the accumulated sums (one CTA)
-  if (blockIdx.x == 0 && blockIdx.y == 0) {
-    const int NO = m.no, NOC = NO * C, NT = m.nt;
-    // bn_qkv
-    for (int ch = tid; ch < 2 * C; ch += 256) {
-      double dg = 0.0, db = 0.0;
-      for (int g = 0; g < m.ngroups; ++g) {
-        const double* st_ = stats + (size_t)g * m.nstat_f;
-        const double* bs_ = bstats + (size_t)g * m.nstat_b;
-        const double n = (double)m.Bg * m.L, s1 = bs_[m.b_qkv_s1 + ch], s2 = bs_[m.b_qkv_s2 + ch];
-        if (m.training) {
-          double mu = st_[m.f_qkv_sum + ch] / n, var = st_[m.f_qkv_sq + ch] / n - mu * mu;
-          if (var < 0.0) var = 0.0;
-          dg += (s2 - mu * s1) / sqrt(var + (double)m.eps);
-        } else {
-          dg += (s2 - (double)p.bn_qkv_rm[ch] * s1) / sqrt((double)p.bn_qkv_rv[ch] + (double)m.eps);
-        }
-        db += s1;
-      }
-      if (gr.dbn_qkv_w) gr.dbn_qkv_w[ch] = (float)dg;
-      if (gr.dbn_qkv_b) gr.dbn_qkv_b[ch] = (float)db;
-    }
-    // bn_output (+ gates f_sv, f_sve) and bn_similarity (+ gates f_qr, f_kr): per-channel terms into smem
-    double gpart[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int ch = tid; ch < NOC; ch += 256) {
-      const int sidx = NO == 2 ? (ch & 1) : 0;
-      const float f = sidx ? gate_of_b(p.f_sve) : gate_of_b(p.f_sv);
-      const double gam = p.bn_out_w[ch];
-      double dg = 0.0, db = 0.0;
-      for (int g = 0; g < m.ngroups; ++g) {
-        const double* st_ = stats + (size_t)g * m.nstat_f;
-        const double* bs_ = bstats + (size_t)g * m.nstat_b;
-        const double n = (double)m.Bg * m.L, s1 = bs_[m.b_out_s1 + ch / NO], s2 = bs_[m.b_out_s2 + ch];
-        if (m.training) {
-          double mu = st_[m.f_out_sum + ch] / n, var = st_[m.f_out_sq + ch] / n - mu * mu;
-          if (var < 0.0) var = 0.0;
-          const double su2 = (double)f * f * var + (double)m.eps, su = sqrt(su2);
-          dg += (double)f * (s2 - mu * s1) / su;
-          gpart[2 + sidx] += gam * (s2 - mu * s1) * (double)m.eps / (su2 * su);
-        } else {
-          const double inv = 1.0 / sqrt((double)p.bn_out_rv[ch] + (double)m.eps);
-          dg += ((double)f * s2 - (double)p.bn_out_rm[ch] * s1) * inv;
-          gpart[2 + sidx] += gam * inv * s2;
-        }
-        db += s1;
-      }
-      if (gr.dbn_out_w) gr.dbn_out_w[ch] = (float)dg;
-      if (gr.dbn_out_b) gr.dbn_out_b[ch] = (float)db;
-    }
-    if (tid < NT * MT_G) {
-      const int ch = tid, t = ch / MT_G;
-      const float f = t == 0 ? 1.f : (t == 1 ? gate_of_b(p.f_qr) : gate_of_b(p.f_kr));
-      const double gam = p.bn_sim_w[ch];
-      double dg = 0.0;
-      for (int g = 0; g < m.ngroups; ++g) {
-        const double* st_ = stats + (size_t)g * m.nstat_f;
-        const double* bs_ = bstats + (size_t)g * m.nstat_b;
-        const double n = (double)m.Bg * m.L * m.L, T = bs_[m.b_sim_t + ch];
-        if (m.training) {
-          double mu = st_[m.f_sim_sum + ch] / n, var = st_[m.f_sim_sq + ch] / n - mu * mu;
-          if (var < 0.0) var = 0.0;
-          const double su2 = (double)f * f * var + (double)m.eps, su = sqrt(su2);
-          dg += (double)f * T / su;
-          if (t > 0) gpart[t - 1] += gam * T * (double)m.eps / (su2 * su);
-        } else {
-          const double inv = 1.0 / sqrt((double)p.bn_sim_rv[ch] + (double)m.eps);
-          dg += (double)f * T * inv;
-          if (t > 0) gpart[t - 1] += gam * inv * T;
-        }
-      }
-      if (gr.dbn_sim_w) gr.dbn_sim_w[ch] = (float)dg;
-      if (gr.dbn_sim_b) gr.dbn_sim_b[ch] = 0.f;      // sum dZ == 0: softmax is shift invariant
-    }
-    // block-reduce the four gate partials (fixed order -> deterministic)
-    __shared__ double gred[4][256];
-    for (int k = 0; k < 4; ++k) gred[k][tid] = gpart[k];
-    __syncthreads();
-    if (tid < 4 && gr.dgates) {
-      double t = 0.0;
-      for (int k = 0; k < 256; ++k) t += gred[tid][k];
-      gr.dgates[tid] = (float)t;
-    }
-  }
+    for (int k = threadIdx.x; k < nrel; k += blockDim.x) MT_GADD(m, drel + k, dRs[k]);
 }
 
 // ============================================================================ host launcher
+int launch_bwd_gather(const Dims& m, const float* dout, const float* oraw, float* gs, double* bstats,
+                      cudaStream_t st);
+int launch_bwd_proj(const Dims& m, const MtAxialParams& p, const MtAxialGrads& gr, const float* x, const double* stats,
+                    const double* bstats, const float* yraw, const float* dyh, cudaStream_t st);
 static int pow2_le(int x) { int p = 1; while (p * 2 <= x) p *= 2; return p; }
 
 template <typename K>
@@ -588,16 +387,13 @@ int axial_backward_launch(const Dims& m, const MtAxialParams& p, const float* x,
   float* dyh = reinterpret_cast<float*>(ws + m.ws_dyh);
   int nl = 0;
   if (mask == 0x1f) {
-  if (cudaMemsetAsync(bstats, 0, sizeof(double) * (size_t)m.ngroups * m.nstat_b, st) != cudaSuccess) return -1;
+  if (cudaMemsetAsync(bstats, 0, sizeof(double) * (size_t)MT_NREP * m.ngroups * m.nstat_b, st) != cudaSuccess) return -1;
   if (gr.dw_qkv && cudaMemsetAsync(gr.dw_qkv, 0, sizeof(float) * 2 * (size_t)m.C * m.C, st) != cudaSuccess) return -1;
   if (m.pos && gr.drelative &&
       cudaMemsetAsync(gr.drelative, 0, sizeof(float) * 2 * (size_t)m.gp * (2 * m.L - 1), st) != cudaSuccess)
     return -1;
   }
-  if (mask & 1) {
-    k_bwd_gather<<<m.N * m.C, 256, 0, st>>>(m, dout, oraw, gs, bstats);
-    ++nl;
-  }
+  if (mask & 1) nl += launch_bwd_gather(m, dout, oraw, gs, bstats, st);
   int spb = 1;
   while (spb * MT_G * m.L < 256 && spb * 2 <= m.Bg && m.Bg % (spb * 2) == 0) spb *= 2;
   const bool p2 = (m.L & (m.L - 1)) == 0;
@@ -627,18 +423,7 @@ int axial_backward_launch(const Dims& m, const MtAxialParams& p, const float* x,
 #undef CALL_BA
     ++nl;
   }
-  if (mask & 8) {
-    int TS, TL;
-    if (m.axis == 1) { TL = m.L < 64 ? m.L : 64; TS = 64 / TL; if (TS > m.Bg) TS = m.Bg; }
-    else { TS = m.Bg < 8 ? m.Bg : 8; TL = 64 / TS; if (TL > m.L) TL = m.L; }
-    if (TS < 1) TS = 1;
-    const int nTL = (m.L + TL - 1) / TL, nTS = (m.Bg + TS - 1) / TS;
-    dim3 grid(m.ngroups * nTS * nTL, 2 * m.C / 32);
-    const size_t smem = sizeof(float) * (6 * (size_t)m.C + 2 * (size_t)m.C * 64 + (size_t)m.C * 65 + 16 * 64);
-    if (set_smem_b(k_bwd_proj, smem) != cudaSuccess) return -1;
-    k_bwd_proj<<<grid, 256, smem, st>>>(m, p, gr, x, stats, bstats, yraw, dyh, TS, TL, nTS * nTL, nTL);
-    ++nl;
-  }
+  if (mask & 8) nl += launch_bwd_proj(m, p, gr, x, stats, bstats, yraw, dyh, st);
   *nlaunch = nl;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -12,74 +12,14 @@
 // at 512 px) never exists: scores live in registers, one query row per thread.
 #include "common.cuh"
 
-// ============================================================================ k_proj
-// Tile = 64 positions (TS strips x TL consecutive l) x 32 output channels.
-// smem X tile is position-major in strip order (l fastest) so that y_raw stores are
-// contiguous; the NCHW gather for axis 0 is transposed while staging.
-__global__ void __launch_bounds__(256)
-k_proj(Dims m, const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ yraw,
-       double* __restrict__ stats, int TS, int TL, int tiles_per_group, int nTL) {
-  extern __shared__ float Xs[];                       // [C][64]
-  const int tid = threadIdx.x;
-  const int tile = blockIdx.x, grp = tile / tiles_per_group, tin = tile - grp * tiles_per_group;
-  const int ts_idx = tin / nTL, tl_idx = tin - ts_idx * nTL;
-  const int sb0 = ts_idx * TS, l0 = tl_idx * TL, npos = TS * TL;
-  const int C = m.C;
-  for (int idx = tid; idx < C * 64; idx += 256) {
-    int c = idx >> 6, r = idx & 63;
-    if (r >= npos) continue;
-    int s, l;
-    if (m.axis == 0) { s = r % TS; l = r / TS; } else { l = r % TL; s = r / TL; }
-    float v = 0.f;
-    if (sb0 + s < m.Bg && l0 + l < m.L) v = __ldg(x + nchw_addr(m, grp * m.Bg + sb0 + s, c, l0 + l));
-    Xs[c * 64 + s * TL + l] = v;
-  }
-  __syncthreads();
-  const int pos = tid & 63, ocl = tid >> 6;
-  const int s = pos / TL, l = pos - s * TL;
-  const bool valid = pos < npos && sb0 + s < m.Bg && l0 + l < m.L;
-  const int oc0 = blockIdx.y * 32 + ocl * 8;
-  float acc[8];
-#pragma unroll
-  for (int o = 0; o < 8; ++o) acc[o] = 0.f;
-  if (pos < npos) {
-    for (int c = 0; c < C; c += 4) {
-      float x0 = Xs[(c + 0) * 64 + pos], x1 = Xs[(c + 1) * 64 + pos];
-      float x2 = Xs[(c + 2) * 64 + pos], x3 = Xs[(c + 3) * 64 + pos];
-#pragma unroll
-      for (int o = 0; o < 8; ++o) {
-        float4 wv = __ldg(reinterpret_cast<const float4*>(w + (size_t)(oc0 + o) * C + c));
-        acc[o] = fmaf(wv.x, x0, fmaf(wv.y, x1, fmaf(wv.z, x2, fmaf(wv.w, x3, acc[o]))));
-      }
-    }
-  }
-  const int b = grp * m.Bg + sb0 + s;
-  if (valid) {
-#pragma unroll
-    for (int o = 0; o < 8; ++o) yraw[((size_t)b * 2 * C + oc0 + o) * m.L + l0 + l] = acc[o];
-  }
-  if (m.training) {
-    double* st = stats + (size_t)grp * m.nstat_f;
-#pragma unroll
-    for (int o = 0; o < 8; ++o) {
-      float v = valid ? acc[o] : 0.f;
-      float s1 = seg_sum(v, 32), s2 = seg_sum(v * v, 32);
-      if ((tid & 31) == 0) {
-        atomicAdd(st + m.f_qkv_sum + oc0 + o, (double)s1);
-        atomicAdd(st + m.f_qkv_sq + oc0 + o, (double)s2);
-      }
-    }
-  }
-}
-
 // ============================================================================ shared loaders
 // qkv BN coefficients (y_hat = a*y_raw + b) for all 2C channels of statistic group `grp`
 __device__ __forceinline__ void load_qkv_coef(const Dims& m, const MtAxialParams& p, const double* stats, int grp,
                                               float* ca, float* cb) {
-  const double* st = stats + (size_t)grp * m.nstat_f;
   const double n = (double)m.Bg * m.L;
   for (int ch = threadIdx.x; ch < 2 * m.C; ch += blockDim.x) {
-    BnCoef c = bn_coef(m.training, m.training ? st[m.f_qkv_sum + ch] : 0.0, m.training ? st[m.f_qkv_sq + ch] : 0.0, n,
+    BnCoef c = bn_coef(m.training, m.training ? stat_get(m, stats, grp, m.nstat_f, m.f_qkv_sum + ch) : 0.0,
+                       m.training ? stat_get(m, stats, grp, m.nstat_f, m.f_qkv_sq + ch) : 0.0, n,
                        1.f, p.bn_qkv_w[ch], p.bn_qkv_b[ch], p.bn_qkv_rm[ch], p.bn_qkv_rv[ch], m.eps);
     ca[ch] = c.a; cb[ch] = c.b;
   }
@@ -107,11 +47,11 @@ __device__ __forceinline__ float gate_of(const float* p) { return p ? __ldg(p) :
 // softmax-side weight of similarity term t, head g:  a_t = gamma*f/sqrt(f^2 var + eps)
 __device__ __forceinline__ BnCoef sim_coef(const Dims& m, const MtAxialParams& p, const double* stats, int grp, int t,
                                            int g) {
-  const double* st = stats + (size_t)grp * m.nstat_f;
   const int ch = t * MT_G + g;
   const float f = t == 0 ? 1.f : (t == 1 ? gate_of(p.f_qr) : gate_of(p.f_kr));
   const double n = (double)m.Bg * m.L * m.L;
-  return bn_coef(m.training, m.training ? st[m.f_sim_sum + ch] : 0.0, m.training ? st[m.f_sim_sq + ch] : 0.0, n, f,
+  return bn_coef(m.training, m.training ? stat_get(m, stats, grp, m.nstat_f, m.f_sim_sum + ch) : 0.0,
+                 m.training ? stat_get(m, stats, grp, m.nstat_f, m.f_sim_sq + ch) : 0.0, n, f,
                  p.bn_sim_w[ch], p.bn_sim_b[ch], p.bn_sim_rm[ch], p.bn_sim_rv[ch], m.eps);
 }
 
@@ -172,16 +112,16 @@ k_sim_stats(Dims m, MtAxialParams p, const float* __restrict__ yraw, double* __r
     }
   }
   __syncthreads();
-  double* st = stats + (size_t)grp * m.nstat_f;
+  double* st = stat_slot(m, stats, grp, m.nstat_f, blockIdx.x);
   if (threadIdx.x < m.nt * MT_G) {
-    atomicAdd(st + m.f_sim_sum + threadIdx.x, (double)red[threadIdx.x * 2 + 0]);
-    atomicAdd(st + m.f_sim_sq + threadIdx.x, (double)red[threadIdx.x * 2 + 1]);
+    MT_GADD(m, st + m.f_sim_sum + threadIdx.x, (double)red[threadIdx.x * 2 + 0]);
+    MT_GADD(m, st + m.f_sim_sq + threadIdx.x, (double)red[threadIdx.x * 2 + 1]);
   }
   // running statistics of bn_qkv: one CTA, sequential EMA over the statistic groups
   if (blockIdx.x == 0) {
     const double n = (double)m.Bg * L;
     for (int ch = threadIdx.x; ch < 2 * C; ch += blockDim.x)
-      ema_update(p.bn_qkv_rm, p.bn_qkv_rv, ch, stats, m.nstat_f, m.f_qkv_sum, m.f_qkv_sq, m.ngroups, n, 1.f, m.momentum);
+      ema_update(m, p.bn_qkv_rm, p.bn_qkv_rv, ch, stats, m.nstat_f, m.f_qkv_sum, m.f_qkv_sq, n, 1.f);
   }
 }
 
@@ -281,68 +221,27 @@ k_attn(Dims m, MtAxialParams p, const float* __restrict__ yraw, double* __restri
   }
   if (m.training) {
     __syncthreads();
-    double* st = stats + (size_t)grp * m.nstat_f;
+    double* st = stat_slot(m, stats, grp, m.nstat_f, blockIdx.x);
     for (int ch = threadIdx.x; ch < NO * C; ch += blockDim.x) {
-      atomicAdd(st + m.f_out_sum + ch, (double)red[ch * 2]);
-      atomicAdd(st + m.f_out_sq + ch, (double)red[ch * 2 + 1]);
+      MT_GADD(m, st + m.f_out_sum + ch, (double)red[ch * 2]);
+      MT_GADD(m, st + m.f_out_sq + ch, (double)red[ch * 2 + 1]);
     }
     if (blockIdx.x == 0) {                 // running statistics of bn_similarity
       const double n = (double)m.Bg * L * L;
       for (int ch = threadIdx.x; ch < m.nt * MT_G; ch += blockDim.x) {
         const int t = ch / MT_G;
         const float f = t == 0 ? 1.f : (t == 1 ? gate_of(p.f_qr) : gate_of(p.f_kr));
-        ema_update(p.bn_sim_rm, p.bn_sim_rv, ch, stats, m.nstat_f, m.f_sim_sum, m.f_sim_sq, m.ngroups, n, f, m.momentum);
+        ema_update(m, p.bn_sim_rm, p.bn_sim_rv, ch, stats, m.nstat_f, m.f_sim_sum, m.f_sim_sq, n, f);
       }
-    }
-  }
-}
-
-// ============================================================================ k_out
-// One CTA per (n, c) plane: BN(bn_output) as a per-channel affine map of the raw sv/sve,
-// pair sum, un-permute to NCHW, AvgPool2d(stride).
-__global__ void __launch_bounds__(256)
-k_out(Dims m, MtAxialParams p, const double* __restrict__ stats, const float* __restrict__ oraw,
-      float* __restrict__ out) {
-  __shared__ float sa[2], sb[2];
-  const int n = blockIdx.x / m.C, c = blockIdx.x - n * m.C;
-  const int grp = n / (m.N / m.ngroups);
-  const int NO = m.no, L = m.L;
-  if (threadIdx.x < NO) {
-    const int ch = c * NO + threadIdx.x;
-    const double* st = stats + (size_t)grp * m.nstat_f;
-    const float f = threadIdx.x == 0 ? gate_of(p.f_sv) : gate_of(p.f_sve);
-    BnCoef k = bn_coef(m.training, m.training ? st[m.f_out_sum + ch] : 0.0, m.training ? st[m.f_out_sq + ch] : 0.0,
-                       (double)m.Bg * L, f, p.bn_out_w[ch], p.bn_out_b[ch], p.bn_out_rm[ch], p.bn_out_rv[ch], m.eps);
-    sa[threadIdx.x] = k.a; sb[threadIdx.x] = k.b;
-  }
-  __syncthreads();
-  const float a0 = sa[0], a1 = NO == 2 ? sa[1] : 0.f, bsum = sb[0] + (NO == 2 ? sb[1] : 0.f);
-  const int st_ = m.stride, Ho = m.H / st_, Wo = m.W / st_;
-  const float inv = 1.f / (float)(st_ * st_);
-  for (int idx = threadIdx.x; idx < Ho * Wo; idx += blockDim.x) {
-    const int ho = idx / Wo, wo = idx - ho * Wo;
-    float acc = 0.f;
-    for (int dh = 0; dh < st_; ++dh)
-      for (int dw = 0; dw < st_; ++dw) {
-        const int h = ho * st_ + dh, w = wo * st_ + dw;
-        const int b = m.axis == 0 ? n * m.W + w : n * m.H + h;
-        const int l = m.axis == 0 ? h : w;
-        const float* o = oraw + ((size_t)b * NO * m.C + c * NO) * L + l;
-        acc = fmaf(a0, __ldg(o), acc);
-        if (NO == 2) acc = fmaf(a1, __ldg(o + L), acc);
-      }
-    out[((size_t)blockIdx.x * Ho + ho) * Wo + wo] = fmaf(acc, inv, bsum);
-  }
-  if (m.training && blockIdx.x == 0) {     // running statistics of bn_output
-    const double cnt = (double)m.Bg * L;
-    for (int ch = threadIdx.x; ch < NO * m.C; ch += blockDim.x) {
-      const float f = (NO == 2 && (ch & 1)) ? gate_of(p.f_sve) : gate_of(p.f_sv);
-      ema_update(p.bn_out_rm, p.bn_out_rv, ch, stats, m.nstat_f, m.f_out_sum, m.f_out_sq, m.ngroups, cnt, f, m.momentum);
     }
   }
 }
 
 // ============================================================================ host launchers
+int launch_proj(const Dims& m, const float* x, const float* w, float* yraw, double* stats, cudaStream_t st);
+int launch_out(const Dims& m, const MtAxialParams& p, const double* stats, const float* oraw, float* out,
+               cudaStream_t st);
+
 struct LaunchPlan { int SPB, segw; size_t smem_attn; };
 
 static int pow2_floor(int x) { int p = 1; while (p * 2 <= x) p *= 2; return p; }
@@ -385,20 +284,9 @@ int axial_forward_launch(const Dims& m, const MtAxialParams& p, const float* x, 
   float* lse = reinterpret_cast<float*>(saved + m.sv_lse);
   int nl = 0;
   if (m.training && mask == 0x1f) {
-    if (cudaMemsetAsync(stats, 0, sizeof(double) * (size_t)m.ngroups * m.nstat_f, st) != cudaSuccess) return -1;
+    if (cudaMemsetAsync(stats, 0, sizeof(double) * (size_t)MT_NREP * m.ngroups * m.nstat_f, st) != cudaSuccess) return -1;
   }
-  if (mask & 1) {  // k_proj
-    int TS, TL;
-    if (m.axis == 1) { TL = m.L < 64 ? m.L : 64; TS = 64 / TL; if (TS > m.Bg) TS = m.Bg; }
-    else { TS = m.Bg < 8 ? m.Bg : 8; TL = 64 / TS; if (TL > m.L) TL = m.L; }
-    if (TS < 1) TS = 1;
-    const int nTL = (m.L + TL - 1) / TL, nTS = (m.Bg + TS - 1) / TS;
-    dim3 grid(m.ngroups * nTS * nTL, 2 * m.C / 32);
-    const size_t smem = (size_t)m.C * 64 * sizeof(float);
-    if (set_smem(k_proj, smem) != cudaSuccess) return -1;
-    k_proj<<<grid, 256, smem, st>>>(m, x, p.w_qkv, yraw, stats, TS, TL, nTS * nTL, nTL);
-    ++nl;
-  }
+  if (mask & 1) nl += launch_proj(m, x, p.w_qkv, yraw, stats, st);
   if (m.training && (mask & 2)) {
     LaunchPlan pl = plan_attn(m, 0, 48);
     if (pl.smem_attn > 227 * 1024) return -2;
@@ -419,10 +307,7 @@ int axial_forward_launch(const Dims& m, const MtAxialParams& p, const float* x, 
 #undef CALL_ATTN
     ++nl;
   }
-  if (mask & 8) {
-    k_out<<<m.N * m.C, 256, 0, st>>>(m, p, stats, oraw, out);
-    ++nl;
-  }
+  if (mask & 8) nl += launch_out(m, p, stats, oraw, out, st);
   *nlaunch = nl;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -1,0 +1,400 @@
+// axial_proj.cu -- the three projection GEMMs of the axial op as one register-tiled fp32
+// SGEMM core (64 x 64 output tile, 256 threads, 4 x 4 per thread, K chunks of 16):
+//
+//   k_proj       Y[2C x P]  = W[2C x C] . X[C x P]        (+ fp64 sum / sumsq per output channel)
+//   k_bwd_dx     dX[C x P]  = W^T[C x 2C] . dY[2C x P]     (bn_qkv backward applied while loading dY)
+//   k_bwd_dw     dW[2C x C] += dY[2C x Pk] . X^T[Pk x C]   (split over position chunks, atomics)
+//
+// P = B*L positions.  X lives in NCHW (reference conv1d on permuted strips, axialnet.py:143-151),
+// Y / dY in strip-major [B][2C][L]; a position tile is TS strips x TL consecutive l so that both
+// sides move in >= 32-byte runs.  fp32 FFMA on purpose: tf32/bf16 operands break the 1e-2
+// train-mode parity budget (DESIGN.md "precision"); a 3xTF32 tcgen05 version is future work.
+#include "common.cuh"
+
+namespace {
+
+struct PosTile {           // decode of a 64-position tile
+  int grp, sb0, l0, TS, TL, npos;
+};
+
+__device__ __forceinline__ PosTile pos_tile(const Dims& m, int tile, int TS, int TL, int tiles_per_group, int nTL) {
+  PosTile t;
+  t.grp = tile / tiles_per_group;
+  const int tin = tile - t.grp * tiles_per_group;
+  const int ts_idx = tin / nTL, tl_idx = tin - ts_idx * nTL;
+  t.sb0 = ts_idx * TS; t.l0 = tl_idx * TL; t.TS = TS; t.TL = TL; t.npos = TS * TL;
+  return t;
+}
+
+// position slot r (0..63) -> (strip-in-tile, l-in-tile); "x order" is NCHW friendly for axis 0
+__device__ __forceinline__ void slot_x(const Dims& m, const PosTile& t, int r, int& s, int& l) {
+  if (m.axis == 0) { s = r % t.TS; l = r / t.TS; } else { l = r % t.TL; s = r / t.TL; }
+}
+__device__ __forceinline__ bool slot_ok(const Dims& m, const PosTile& t, int r, int s, int l) {
+  return r < t.npos && t.sb0 + s < m.Bg && t.l0 + l < m.L;
+}
+
+// 64x64x16 micro-kernel step on smem tiles As[16][64+pad] (k-major), Bs[16][64+pad]
+#define TILE_LD 68
+__device__ __forceinline__ void mma_chunk(const float* As, const float* Bs, int ty, int tx, float acc[4][4], int kc) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    if (k >= kc) break;
+    const float4 a = *reinterpret_cast<const float4*>(As + k * TILE_LD + ty * 4);
+    const float4 b = *reinterpret_cast<const float4*>(Bs + k * TILE_LD + tx * 4);
+    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+  }
+}
+
+}  // namespace
+
+// ============================================================================ k_proj
+// grid (position tiles, ceil(2C/64)).  M = oc (ty), N = position (tx).
+__global__ void __launch_bounds__(256)
+k_proj(Dims m, const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ yraw,
+       double* __restrict__ stats, int TS, int TL, int tiles_per_group, int nTL) {
+  __shared__ __align__(16) float As[16 * TILE_LD];
+  __shared__ __align__(16) float Bs[16 * TILE_LD];
+  __shared__ float red[64][2];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int C = m.C, M = 2 * C;
+  const PosTile t = pos_tile(m, blockIdx.x, TS, TL, tiles_per_group, nTL);
+  const int oc0 = blockIdx.y * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  if (tid < 64) { red[tid][0] = 0.f; red[tid][1] = 0.f; }
+  for (int k0 = 0; k0 < C; k0 += 16) {
+    // A chunk: W[oc0 + mm][k0 + kk] -> As[kk][mm]   (each thread: one float4 of 4 consecutive k)
+    {
+      const int mm = tid >> 2, kq = (tid & 3) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (oc0 + mm < M && k0 + kq < C) v = __ldg(reinterpret_cast<const float4*>(w + (size_t)(oc0 + mm) * C + k0 + kq));
+      As[(kq + 0) * TILE_LD + mm] = v.x; As[(kq + 1) * TILE_LD + mm] = v.y;
+      As[(kq + 2) * TILE_LD + mm] = v.z; As[(kq + 3) * TILE_LD + mm] = v.w;
+    }
+    // B chunk: X[k0 + kk][pos r] gathered from NCHW in x order, stored in strip order (l fastest)
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int idx = tid + it * 256, kk = idx >> 6, r = idx & 63;
+      int s, l;
+      slot_x(m, t, r, s, l);
+      float v = 0.f;
+      if (slot_ok(m, t, r, s, l) && k0 + kk < C)
+        v = __ldg(x + nchw_addr(m, t.grp * m.Bg + t.sb0 + s, k0 + kk, t.l0 + l));
+      if (r < t.npos) Bs[kk * TILE_LD + s * t.TL + l] = v; else Bs[kk * TILE_LD + r] = 0.f;
+    }
+    __syncthreads();
+    mma_chunk(As, Bs, ty, tx, acc, C - k0 < 16 ? C - k0 : 16);
+    __syncthreads();
+  }
+  // epilogue: thread owns oc = oc0 + ty*4 + i, positions tx*4 + j (strip order)
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int pos = tx * 4 + j, s = pos / t.TL, l = pos - s * t.TL;
+    const bool ok = pos < t.npos && t.sb0 + s < m.Bg && t.l0 + l < m.L;
+    if (!ok) continue;
+    const int b = t.grp * m.Bg + t.sb0 + s;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int oc = oc0 + ty * 4 + i;
+      if (oc < M) {
+        yraw[((size_t)b * M + oc) * m.L + t.l0 + l] = acc[i][j];
+        s1[i] += acc[i][j]; s2[i] = fmaf(acc[i][j], acc[i][j], s2[i]);
+      }
+    }
+  }
+  if (m.training) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {           // reduce over the 16 tx lanes that share this oc
+      float a = seg_sum(s1[i], 16), b2 = seg_sum(s2[i], 16);
+      if (tx == 0) { red[ty * 4 + i][0] = a; red[ty * 4 + i][1] = b2; }
+    }
+    __syncthreads();
+    if (tid < 64 && oc0 + tid < M) {
+      double* st = stat_slot(m, stats, t.grp, m.nstat_f, blockIdx.x);
+      MT_GADD(m, st + m.f_qkv_sum + oc0 + tid, (double)red[tid][0]);
+      MT_GADD(m, st + m.f_qkv_sq + oc0 + tid, (double)red[tid][1]);
+    }
+  }
+}
+
+// ============================================================================ k_bwd_dx
+// grid (position tiles, ceil(C/64)).  M = c (ty), N = position (tx), K = 2C.
+// CTA (0,0) also emits every BN-parameter / gate gradient from the fp64 sums.
+__device__ void bwd_param_grads(const Dims& m, const MtAxialParams& p, const MtAxialGrads& gr,
+                                const double* stats, const double* bstats);
+
+__global__ void __launch_bounds__(256)
+k_bwd_dx(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stats,
+         const double* __restrict__ bstats, const float* __restrict__ yraw, const float* __restrict__ dyh,
+         int TS, int TL, int tiles_per_group, int nTL) {
+  extern __shared__ __align__(16) float smx[];
+  float* As = smx;                          // [16][TILE_LD]
+  float* Bs = As + 16 * TILE_LD;            // [16][TILE_LD]
+  float* qA = Bs + 16 * TILE_LD;            // [2C] x 3 bn_qkv backward coefficients
+  float* qB = qA + 2 * m.C;
+  float* qC = qB + 2 * m.C;
+  float* Ts = qC + 2 * m.C;                 // [64][65] output staging (transposed store)
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int C = m.C, K = 2 * C;
+  const PosTile t = pos_tile(m, blockIdx.x, TS, TL, tiles_per_group, nTL);
+  const int c0 = blockIdx.y * 64;
+  for (int ch = tid; ch < K; ch += 256) {
+    const double n = (double)m.Bg * m.L;
+    BnBwdCoef k = bn_bwd_coef(m.training, m.training ? stat_get(m, stats, t.grp, m.nstat_f, m.f_qkv_sum + ch) : 0.0,
+                              m.training ? stat_get(m, stats, t.grp, m.nstat_f, m.f_qkv_sq + ch) : 0.0, n, 1.f,
+                              p.bn_qkv_w[ch], p.bn_qkv_rv[ch], m.eps,
+                              m.training ? stat_get(m, bstats, t.grp, m.nstat_b, m.b_qkv_s1 + ch) : 0.0,
+                              m.training ? stat_get(m, bstats, t.grp, m.nstat_b, m.b_qkv_s2 + ch) : 0.0);
+    qA[ch] = k.A; qB[ch] = k.Bc; qC[ch] = k.Cc;
+  }
+  __syncthreads();
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    // A chunk: W^T: As[kk][mm] = W[k0+kk][c0+mm]  (row of W is contiguous in c)
+    {
+      const int kk = tid >> 4, mq = (tid & 15) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + kk < K && c0 + mq < C) v = __ldg(reinterpret_cast<const float4*>(p.w_qkv + (size_t)(k0 + kk) * C + c0 + mq));
+      *reinterpret_cast<float4*>(As + kk * TILE_LD + mq) = v;
+    }
+    // B chunk: dy_raw[k0+kk][pos] = A*dyh + Bc + Cc*yraw, strip order (contiguous TL-runs)
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int idx = tid + it * 256, kk = idx >> 6, r = idx & 63;
+      const int s = r / t.TL, l = r - s * t.TL;
+      float v = 0.f;
+      if (r < t.npos && t.sb0 + s < m.Bg && t.l0 + l < m.L && k0 + kk < K) {
+        const int ch = k0 + kk;
+        const size_t a = ((size_t)(t.grp * m.Bg + t.sb0 + s) * K + ch) * m.L + t.l0 + l;
+        v = fmaf(qA[ch], __ldg(dyh + a), fmaf(qC[ch], __ldg(yraw + a), qB[ch]));
+      }
+      Bs[kk * TILE_LD + r] = v;
+    }
+    __syncthreads();
+    mma_chunk(As, Bs, ty, tx, acc, K - k0 < 16 ? K - k0 : 16);
+    __syncthreads();
+  }
+  // stage (c, pos) tile and store to NCHW with x-order threads (coalesced along the contiguous axis)
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Ts[(ty * 4 + i) * 65 + tx * 4 + j] = acc[i][j];
+  __syncthreads();
+  if (gr.dx) {
+    for (int idx = tid; idx < 64 * 64; idx += 256) {
+      const int cc = idx >> 6, r = idx & 63;
+      if (c0 + cc >= C || r >= t.npos) continue;
+      int s, l;
+      slot_x(m, t, r, s, l);
+      if (t.sb0 + s < m.Bg && t.l0 + l < m.L)
+        gr.dx[nchw_addr(m, t.grp * m.Bg + t.sb0 + s, c0 + cc, t.l0 + l)] = Ts[cc * 65 + s * t.TL + l];
+    }
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0) bwd_param_grads(m, p, gr, stats, bstats);
+}
+
+// ============================================================================ k_bwd_dw
+// grid (ceil(2C/64), ceil(C/64), KSPLIT).  M = oc (ty), N = c (tx), K = positions of this split.
+__global__ void __launch_bounds__(256)
+k_bwd_dw(Dims m, MtAxialParams p, MtAxialGrads gr, const float* __restrict__ x, const double* __restrict__ stats,
+         const double* __restrict__ bstats, const float* __restrict__ yraw, const float* __restrict__ dyh,
+         int TS, int TL, int tiles_per_group, int nTL, int ntiles) {
+  extern __shared__ __align__(16) float smw[];
+  float* Am = smw;                          // [64 pos][TILE_LD]  (k-major: As[k][m] with k = pos)
+  float* Bm = Am + 64 * TILE_LD;            // [64 pos][TILE_LD]
+  float* qA = Bm + 64 * TILE_LD;
+  float* qB = qA + 2 * m.C;
+  float* qC = qB + 2 * m.C;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int C = m.C, M = 2 * C;
+  const int oc0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  int cur_grp = -1;
+  for (int tile = blockIdx.z; tile < ntiles; tile += gridDim.z) {
+    const PosTile t = pos_tile(m, tile, TS, TL, tiles_per_group, nTL);
+    if (t.grp != cur_grp) {                 // bn_qkv backward coefficients of this statistic group
+      __syncthreads();
+      for (int ch = tid; ch < M; ch += 256) {
+        const double n = (double)m.Bg * m.L;
+        BnBwdCoef k = bn_bwd_coef(m.training, m.training ? stat_get(m, stats, t.grp, m.nstat_f, m.f_qkv_sum + ch) : 0.0,
+                                  m.training ? stat_get(m, stats, t.grp, m.nstat_f, m.f_qkv_sq + ch) : 0.0, n, 1.f,
+                                  p.bn_qkv_w[ch], p.bn_qkv_rv[ch], m.eps,
+                                  m.training ? stat_get(m, bstats, t.grp, m.nstat_b, m.b_qkv_s1 + ch) : 0.0,
+                                  m.training ? stat_get(m, bstats, t.grp, m.nstat_b, m.b_qkv_s2 + ch) : 0.0);
+        qA[ch] = k.A; qB[ch] = k.Bc; qC[ch] = k.Cc;
+      }
+      cur_grp = t.grp;
+      __syncthreads();
+    }
+    // A: dy_raw[oc0+mm][pos r] -> Am[r][mm]  (strip order read, contiguous TL-runs)
+    for (int idx = tid; idx < 64 * 64; idx += 256) {
+      const int mm = idx >> 6, r = idx & 63;
+      const int s = r / t.TL, l = r - s * t.TL;
+      float v = 0.f;
+      if (r < t.npos && t.sb0 + s < m.Bg && t.l0 + l < m.L && oc0 + mm < M) {
+        const int ch = oc0 + mm;
+        const size_t a = ((size_t)(t.grp * m.Bg + t.sb0 + s) * M + ch) * m.L + t.l0 + l;
+        v = fmaf(qA[ch], __ldg(dyh + a), fmaf(qC[ch], __ldg(yraw + a), qB[ch]));
+      }
+      Am[r * TILE_LD + mm] = v;
+    }
+    // B: X[c0+nn][pos] gathered in x order, stored at the strip-order slot
+    for (int idx = tid; idx < 64 * 64; idx += 256) {
+      const int nn = idx >> 6, r = idx & 63;
+      int s, l;
+      slot_x(m, t, r, s, l);
+      float v = 0.f;
+      if (slot_ok(m, t, r, s, l) && c0 + nn < C) v = __ldg(x + nchw_addr(m, t.grp * m.Bg + t.sb0 + s, c0 + nn, t.l0 + l));
+      if (r < t.npos) Bm[(s * t.TL + l) * TILE_LD + nn] = v; else Bm[r * TILE_LD + nn] = 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kb = 0; kb < 64; kb += 16) mma_chunk(Am + kb * TILE_LD, Bm + kb * TILE_LD, ty, tx, acc, 16);
+    __syncthreads();
+  }
+  if (gr.dw_qkv) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int oc = oc0 + ty * 4 + i, c = c0 + tx * 4 + j;
+        if (oc < M && c < C) MT_GADD(m, gr.dw_qkv + (size_t)oc * C + c, acc[i][j]);
+      }
+  }
+}
+
+// ============================================================================ parameter gradients
+__device__ __forceinline__ float gate_p(const float* p) { return p ? __ldg(p) : 1.f; }
+
+__device__ void bwd_param_grads(const Dims& m, const MtAxialParams& p, const MtAxialGrads& gr,
+                                const double* stats, const double* bstats) {
+  const int tid = threadIdx.x, C = m.C, NO = m.no, NOC = NO * C, NT = m.nt;
+  for (int ch = tid; ch < 2 * C; ch += 256) {
+    double dg = 0.0, db = 0.0;
+    for (int g = 0; g < m.ngroups; ++g) {
+      const double n = (double)m.Bg * m.L;
+      const double s1 = stat_get(m, bstats, g, m.nstat_b, m.b_qkv_s1 + ch), s2 = stat_get(m, bstats, g, m.nstat_b, m.b_qkv_s2 + ch);
+      if (m.training) {
+        double mu = stat_get(m, stats, g, m.nstat_f, m.f_qkv_sum + ch) / n;
+        double var = stat_get(m, stats, g, m.nstat_f, m.f_qkv_sq + ch) / n - mu * mu;
+        if (var < 0.0) var = 0.0;
+        dg += (s2 - mu * s1) / sqrt(var + (double)m.eps);
+      } else {
+        dg += (s2 - (double)p.bn_qkv_rm[ch] * s1) / sqrt((double)p.bn_qkv_rv[ch] + (double)m.eps);
+      }
+      db += s1;
+    }
+    if (gr.dbn_qkv_w) gr.dbn_qkv_w[ch] = (float)dg;
+    if (gr.dbn_qkv_b) gr.dbn_qkv_b[ch] = (float)db;
+  }
+  double gpart[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int ch = tid; ch < NOC; ch += 256) {
+    const int sidx = NO == 2 ? (ch & 1) : 0;
+    const float f = sidx ? gate_p(p.f_sve) : gate_p(p.f_sv);
+    const double gam = p.bn_out_w[ch];
+    double dg = 0.0, db = 0.0;
+    for (int g = 0; g < m.ngroups; ++g) {
+      const double n = (double)m.Bg * m.L;
+      const double s1 = stat_get(m, bstats, g, m.nstat_b, m.b_out_s1 + ch / NO), s2 = stat_get(m, bstats, g, m.nstat_b, m.b_out_s2 + ch);
+      if (m.training) {
+        double mu = stat_get(m, stats, g, m.nstat_f, m.f_out_sum + ch) / n;
+        double var = stat_get(m, stats, g, m.nstat_f, m.f_out_sq + ch) / n - mu * mu;
+        if (var < 0.0) var = 0.0;
+        const double su2 = (double)f * f * var + (double)m.eps, su = sqrt(su2);
+        dg += (double)f * (s2 - mu * s1) / su;
+        gpart[2 + sidx] += gam * (s2 - mu * s1) * (double)m.eps / (su2 * su);
+      } else {
+        const double inv = 1.0 / sqrt((double)p.bn_out_rv[ch] + (double)m.eps);
+        dg += ((double)f * s2 - (double)p.bn_out_rm[ch] * s1) * inv;
+        gpart[2 + sidx] += gam * inv * s2;
+      }
+      db += s1;
+    }
+    if (gr.dbn_out_w) gr.dbn_out_w[ch] = (float)dg;
+    if (gr.dbn_out_b) gr.dbn_out_b[ch] = (float)db;
+  }
+  if (tid < NT * MT_G) {
+    const int ch = tid, t = ch / MT_G;
+    const float f = t == 0 ? 1.f : (t == 1 ? gate_p(p.f_qr) : gate_p(p.f_kr));
+    const double gam = p.bn_sim_w[ch];
+    double dg = 0.0;
+    for (int g = 0; g < m.ngroups; ++g) {
+      const double n = (double)m.Bg * m.L * m.L, T = stat_get(m, bstats, g, m.nstat_b, m.b_sim_t + ch);
+      if (m.training) {
+        double mu = stat_get(m, stats, g, m.nstat_f, m.f_sim_sum + ch) / n;
+        double var = stat_get(m, stats, g, m.nstat_f, m.f_sim_sq + ch) / n - mu * mu;
+        if (var < 0.0) var = 0.0;
+        const double su2 = (double)f * f * var + (double)m.eps, su = sqrt(su2);
+        dg += (double)f * T / su;
+        if (t > 0) gpart[t - 1] += gam * T * (double)m.eps / (su2 * su);
+      } else {
+        const double inv = 1.0 / sqrt((double)p.bn_sim_rv[ch] + (double)m.eps);
+        dg += (double)f * T * inv;
+        if (t > 0) gpart[t - 1] += gam * inv * T;
+      }
+    }
+    if (gr.dbn_sim_w) gr.dbn_sim_w[ch] = (float)dg;
+    if (gr.dbn_sim_b) gr.dbn_sim_b[ch] = 0.f;        // sum dZ == 0: softmax is shift invariant
+  }
+  __shared__ double gred[4][256];                      // fixed-order block reduce -> deterministic
+  for (int k = 0; k < 4; ++k) gred[k][tid] = gpart[k];
+  __syncthreads();
+  if (tid < 4 && gr.dgates) {
+    double t = 0.0;
+    for (int k = 0; k < 256; ++k) t += gred[tid][k];
+    gr.dgates[tid] = (float)t;
+  }
+}
+
+// ============================================================================ host launchers
+static void proj_tiling(const Dims& m, int& TS, int& TL, int& nTL, int& nTS) {
+  if (m.axis == 1) { TL = m.L < 64 ? m.L : 64; TS = 64 / TL; if (TS > m.Bg) TS = m.Bg; }
+  else { TS = m.Bg < 8 ? m.Bg : 8; TL = 64 / TS; if (TL > m.L) TL = m.L; }
+  if (TS < 1) TS = 1;
+  nTL = (m.L + TL - 1) / TL; nTS = (m.Bg + TS - 1) / TS;
+}
+
+int launch_proj(const Dims& m, const float* x, const float* w, float* yraw, double* stats, cudaStream_t st) {
+  int TS, TL, nTL, nTS;
+  proj_tiling(m, TS, TL, nTL, nTS);
+  dim3 grid(m.ngroups * nTS * nTL, (2 * m.C + 63) / 64);
+  k_proj<<<grid, 256, 0, st>>>(m, x, w, yraw, stats, TS, TL, nTS * nTL, nTL);
+  return 1;
+}
+
+int launch_bwd_proj(const Dims& m, const MtAxialParams& p, const MtAxialGrads& gr, const float* x, const double* stats,
+                    const double* bstats, const float* yraw, const float* dyh, cudaStream_t st) {
+  int TS, TL, nTL, nTS;
+  proj_tiling(m, TS, TL, nTL, nTS);
+  const int ntiles = m.ngroups * nTS * nTL;
+  {
+    dim3 grid(ntiles, (m.C + 63) / 64);
+    const size_t smem = sizeof(float) * (2 * 16 * TILE_LD + 6 * (size_t)m.C + 64 * 65);
+    k_bwd_dx<<<grid, 256, smem, st>>>(m, p, gr, stats, bstats, yraw, dyh, TS, TL, nTS * nTL, nTL);
+  }
+  {
+    int ksplit = ntiles < 32 ? ntiles : 32;
+    dim3 grid((2 * m.C + 63) / 64, (m.C + 63) / 64, ksplit);
+    const size_t smem = sizeof(float) * (2 * 64 * TILE_LD + 6 * (size_t)m.C);
+    cudaFuncSetAttribute(k_bwd_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_bwd_dw<<<grid, 256, smem, st>>>(m, p, gr, x, stats, bstats, yraw, dyh, TS, TL, nTS * nTL, nTL, ntiles);
+  }
+  return 2;
+}

@@ -4,13 +4,16 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "../../include/medt_axial.h"
 
 #define MT_G 8              // heads: fixed by the reference (axialnet.py:400)
 #define MT_LOG2E 1.4426950408889634f
+#define MT_NREP 8           // replicated fp64 accumulator slots (CTA picks blockIdx & 7): cuts same-address atomic serialisation
 
 struct Dims {
   int N, C, H, W, axis, stride, variant, training, ngroups;
+  int dbg;                 // MT_DEBUG_FLAGS env (timing experiments only): bit0 = skip global statistic atomics
   int L, other, B, Bg, gp, d, nt, no, LP, pos;
   float eps, momentum;
   // fp64 statistic accumulator layout (per statistic group)
@@ -27,6 +30,7 @@ static inline bool make_dims(const MtAxialDesc* d, Dims& m) {
   m.N = d->N; m.C = d->C; m.H = d->H; m.W = d->W; m.axis = d->axis; m.stride = d->stride;
   m.variant = d->variant; m.training = d->training; m.ngroups = d->ngroups;
   m.eps = d->eps; m.momentum = d->momentum;
+  { static int flags = -1; if (flags < 0) { const char* e = getenv("MT_DEBUG_FLAGS"); flags = e ? atoi(e) : 0; } m.dbg = flags; }
   if (m.N <= 0 || m.C <= 0 || m.H <= 0 || m.W <= 0 || m.ngroups <= 0) return false;
   if (m.axis != 0 && m.axis != 1) return false;
   if (m.stride < 1 || m.H % m.stride || m.W % m.stride) return false;
@@ -52,13 +56,13 @@ static inline bool make_dims(const MtAxialDesc* d, Dims& m) {
   m.b_qkv_s1 = m.b_sim_t + m.nt * MT_G; m.b_qkv_s2 = m.b_qkv_s1 + 2 * C;
   m.nstat_b = m.b_qkv_s2 + 2 * C;
   size_t off = 0;
-  m.sv_stats = off; off = mt_align(off + sizeof(double) * (size_t)m.ngroups * m.nstat_f);
+  m.sv_stats = off; off = mt_align(off + sizeof(double) * (size_t)MT_NREP * m.ngroups * m.nstat_f);
   m.sv_yraw = off;  off = mt_align(off + sizeof(float) * (size_t)m.B * 2 * C * m.L);
   m.sv_oraw = off;  off = mt_align(off + sizeof(float) * (size_t)m.B * m.no * C * m.L);
   m.sv_lse = off;   off = mt_align(off + sizeof(float) * (size_t)m.B * MT_G * m.L);
   m.sv_bytes = off;
   off = 0;
-  m.ws_bstats = off; off = mt_align(off + sizeof(double) * (size_t)m.ngroups * m.nstat_b);
+  m.ws_bstats = off; off = mt_align(off + sizeof(double) * (size_t)MT_NREP * m.ngroups * m.nstat_b);
   m.ws_gs = off;     off = mt_align(off + sizeof(float) * (size_t)m.B * C * m.L);
   m.ws_dyh = off;    off = mt_align(off + sizeof(float) * (size_t)m.B * 2 * C * m.L);
   m.ws_bytes = off;
@@ -135,12 +139,24 @@ __device__ __forceinline__ BnBwdCoef bn_bwd_coef(int training, double sum, doubl
   return r;
 }
 
+// replicated accumulators: layout [MT_NREP][ngroups][nstat]
+__device__ __forceinline__ double* stat_slot(const Dims& m, double* base, int grp, int nstat, int cta) {
+  return base + ((size_t)(cta & (MT_NREP - 1)) * m.ngroups + grp) * nstat;
+}
+__device__ __forceinline__ double stat_get(const Dims& m, const double* base, int grp, int nstat, int off) {
+  double s = 0.0;
+#pragma unroll
+  for (int r = 0; r < MT_NREP; ++r) s += base[((size_t)r * m.ngroups + grp) * nstat + off];
+  return s;
+}
+
 // sequential EMA of the running statistics over the statistic groups (one BN call each)
-__device__ __forceinline__ void ema_update(float* rm, float* rv, int ch, const double* stats, int nstat,
-                                           int off_sum, int off_sq, int ngroups, double n, float f, float mom) {
+__device__ __forceinline__ void ema_update(const Dims& m, float* rm, float* rv, int ch, const double* stats, int nstat,
+                                           int off_sum, int off_sq, double n, float f) {
   float m_ = rm[ch], v_ = rv[ch];
-  for (int g = 0; g < ngroups; ++g) {
-    double sum = stats[(size_t)g * nstat + off_sum + ch], sq = stats[(size_t)g * nstat + off_sq + ch];
+  const float mom = m.momentum;
+  for (int g = 0; g < m.ngroups; ++g) {
+    double sum = stat_get(m, stats, g, nstat, off_sum + ch), sq = stat_get(m, stats, g, nstat, off_sq + ch);
     double mu = sum / n, var = sq / n - mu * mu;
     if (var < 0.0) var = 0.0;
     double mu_u = f * mu, var_u = (double)f * f * var * (n / (n - 1.0));
@@ -149,3 +165,6 @@ __device__ __forceinline__ void ema_update(float* rm, float* rv, int ch, const d
   }
   rm[ch] = m_; rv[ch] = v_;
 }
+
+// global (cross-CTA) statistic accumulation; skipped only by the MT_DEBUG_FLAGS timing experiment
+#define MT_GADD(m, ptr, val) do { if (!((m).dbg & 1)) atomicAdd((ptr), (val)); } while (0)
