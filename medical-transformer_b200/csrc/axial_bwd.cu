@@ -11,8 +11,6 @@
 // P and dZ are recomputed from q,k,v and the saved log-sum-exp; no L x L tensor is stored.
 #include "common.cuh"
 
-__device__ __forceinline__ float gate_of_b(const float* p) { return p ? __ldg(p) : 1.f; }
-
 // ============================================================================ shared loaders
 struct BwdSmem {
   float *ca, *cb, *wsim, *sA, *sB, *sC, *oA, *oB, *oC, *red, *Yn, *R, *dOs, *Dl, *lses;
@@ -42,42 +40,23 @@ static size_t bwd_smem_floats(const Dims& m, int SPB, int nred) {
 //   normalised q,k,v ; relative ; dO (grad w.r.t. raw sv / sve, i.e. after bn_output backward
 //   and the gates) ; D_i = sum_c dO . O ; log-sum-exp ; softmax weights.
 __device__ __forceinline__ void bwd_load(const Dims& m, const MtAxialParams& p, const BwdSmem& s, int b0, int SPB,
-                                         int grp, const double* __restrict__ stats, const double* __restrict__ bstats,
+                                         int grp, const float* __restrict__ coef, const float* __restrict__ bcoef,
                                          const float* __restrict__ yraw, const float* __restrict__ oraw,
                                          const float* __restrict__ lse, const float* __restrict__ gs,
                                          bool need_sim_bwd) {
   const int C = m.C, L = m.L, LP = m.LP, NO = m.no, NOC = NO * C;
-#define ST(off) stat_get(m, stats, grp, m.nstat_f, (off))
-#define BS(off) stat_get(m, bstats, grp, m.nstat_b, (off))
   {
-    const double n = (double)m.Bg * L;
-    for (int ch = threadIdx.x; ch < 2 * C; ch += blockDim.x) {
-      BnCoef c = bn_coef(m.training, m.training ? ST(m.f_qkv_sum + ch) : 0.0, m.training ? ST(m.f_qkv_sq + ch) : 0.0, n,
-                         1.f, p.bn_qkv_w[ch], p.bn_qkv_b[ch], p.bn_qkv_rm[ch], p.bn_qkv_rv[ch], m.eps);
-      s.ca[ch] = c.a; s.cb[ch] = c.b;
-    }
-    for (int ch = threadIdx.x; ch < NOC; ch += blockDim.x) {
-      const float f = (NO == 2 && (ch & 1)) ? gate_of_b(p.f_sve) : gate_of_b(p.f_sv);
-      BnBwdCoef k = bn_bwd_coef(m.training, m.training ? ST(m.f_out_sum + ch) : 0.0,
-                                m.training ? ST(m.f_out_sq + ch) : 0.0, n, f, p.bn_out_w[ch], p.bn_out_rv[ch], m.eps,
-                                m.training ? BS(m.b_out_s1 + ch / NO) : 0.0, m.training ? BS(m.b_out_s2 + ch) : 0.0);
-      s.oA[ch] = k.A; s.oB[ch] = k.Bc; s.oC[ch] = k.Cc;
-    }
+    const float* tq = coef + (size_t)grp * m.ncoef_f + m.cf_q;
+    for (int ch = threadIdx.x; ch < 2 * C; ch += blockDim.x) { s.ca[ch] = tq[2 * ch]; s.cb[ch] = tq[2 * ch + 1]; }
+    const float* to = bcoef + (size_t)grp * m.ncoef_b + m.cb_o;
+    for (int ch = threadIdx.x; ch < NOC; ch += blockDim.x) { s.oA[ch] = to[3 * ch]; s.oB[ch] = to[3 * ch + 1]; s.oC[ch] = to[3 * ch + 2]; }
   }
   if (threadIdx.x < m.nt * MT_G) {
-    const int t = threadIdx.x / MT_G, ch = threadIdx.x;
-    const float f = t == 0 ? 1.f : (t == 1 ? gate_of_b(p.f_qr) : gate_of_b(p.f_kr));
-    const double n = (double)m.Bg * L * L;
-    const double sum = m.training ? ST(m.f_sim_sum + ch) : 0.0, sq = m.training ? ST(m.f_sim_sq + ch) : 0.0;
-    BnCoef c = bn_coef(m.training, sum, sq, n, f, p.bn_sim_w[ch], p.bn_sim_b[ch], p.bn_sim_rm[ch], p.bn_sim_rv[ch], m.eps);
-    s.wsim[ch] = c.a * MT_LOG2E;
+    const int ch = threadIdx.x;
+    s.wsim[ch] = coef[(size_t)grp * m.ncoef_f + m.cf_s + 2 * ch];
     if (need_sim_bwd) {
-      // dy = dZ for every term; sum dZ == 0 exactly (softmax rows), so s1 = 0, s2 = T
-      BnBwdCoef k = bn_bwd_coef(m.training, sum, sq, n, f, p.bn_sim_w[ch], p.bn_sim_rv[ch], m.eps, 0.0,
-                                BS(m.b_sim_t + ch));
-#undef ST
-#undef BS
-      s.sA[ch] = k.A; s.sB[ch] = k.Bc; s.sC[ch] = k.Cc;
+      const float* ts = bcoef + (size_t)grp * m.ncoef_b + m.cb_s + 3 * ch;
+      s.sA[ch] = ts[0]; s.sB[ch] = ts[1]; s.sC[ch] = ts[2];
     }
   }
   if (m.pos) {
@@ -161,6 +140,7 @@ struct PairEval {
 template <int D, bool POS>
 __global__ void __launch_bounds__(256)
 k_bwd_simstats(Dims m, MtAxialParams p, const double* __restrict__ stats, double* __restrict__ bstats,
+               const float* __restrict__ coef, float* __restrict__ bcoef, unsigned* __restrict__ bcnt,
                const float* __restrict__ yraw, const float* __restrict__ oraw, const float* __restrict__ lse,
                const float* __restrict__ gs, int SPB, int segw) {
   constexpr int GP = 2 * D;
@@ -169,7 +149,7 @@ k_bwd_simstats(Dims m, MtAxialParams p, const double* __restrict__ stats, double
   const int b0 = blockIdx.x * SPB, grp = b0 / m.Bg;
   BwdSmem s = carve(m, sm, SPB, 24);
   if (threadIdx.x < 24) s.red[threadIdx.x] = 0.f;
-  bwd_load(m, p, s, b0, SPB, grp, stats, bstats, yraw, oraw, lse, gs, false);
+  bwd_load(m, p, s, b0, SPB, grp, coef, bcoef, yraw, oraw, lse, gs, false);
   const int nitems = SPB * MT_G * L;
   for (int base = 0; base < nitems; base += blockDim.x) {
     const int item = base + threadIdx.x;
@@ -198,12 +178,14 @@ k_bwd_simstats(Dims m, MtAxialParams p, const double* __restrict__ stats, double
   __syncthreads();
   if (threadIdx.x < m.nt * MT_G)
     MT_GADD(m, stat_slot(m, bstats, grp, m.nstat_b, blockIdx.x) + m.b_sim_t + threadIdx.x, (double)s.red[threadIdx.x]);
+  if (last_cta_done(bcnt + 1, gridDim.x)) fin_bwd_sim(m, p, stats, bstats, bcoef);
 }
 
 // ============================================================================ k_bwd_attn
 template <int D, bool POS>
 __global__ void __launch_bounds__(256)
-k_bwd_attn(Dims m, MtAxialParams p, const double* __restrict__ stats, double* __restrict__ bstats,
+k_bwd_attn(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stats, double* __restrict__ bstats,
+           const float* __restrict__ coef, float* __restrict__ bcoef, unsigned* __restrict__ bcnt,
            const float* __restrict__ yraw, const float* __restrict__ oraw, const float* __restrict__ lse,
            const float* __restrict__ gs, float* __restrict__ dyh, float* __restrict__ drel, int SPB, int segw) {
   constexpr int GP = 2 * D;
@@ -214,7 +196,7 @@ k_bwd_attn(Dims m, MtAxialParams p, const double* __restrict__ stats, double* __
   BwdSmem s = carve(m, sm, SPB, 4 * C + nrel);      // red: [2C][2] qkv sums, then dR accumulators
   float* dRs = s.red + 4 * C;
   for (int k = threadIdx.x; k < 4 * C + nrel; k += blockDim.x) s.red[k] = 0.f;
-  bwd_load(m, p, s, b0, SPB, grp, stats, bstats, yraw, oraw, lse, gs, true);
+  bwd_load(m, p, s, b0, SPB, grp, coef, bcoef, yraw, oraw, lse, gs, true);
   const int nitems = SPB * MT_G * L;
 
   // ---- rows: dq[c,i] = sum_j dS_qk k[c,j] + dS_qr Rq[c,i-j]
@@ -352,13 +334,18 @@ k_bwd_attn(Dims m, MtAxialParams p, const double* __restrict__ stats, double* __
   }
   if (POS)
     for (int k = threadIdx.x; k < nrel; k += blockDim.x) MT_GADD(m, drel + k, dRs[k]);
+  // last CTA: bn_qkv backward coefficients for the projection GEMMs + every BN / gate parameter gradient
+  if (last_cta_done(bcnt + 2, gridDim.x)) {
+    fin_bwd_qkv(m, p, stats, bstats, bcoef);
+    bwd_param_grads(m, p, gr, stats, bstats);
+  }
 }
 
 // ============================================================================ host launcher
-int launch_bwd_gather(const Dims& m, const float* dout, const float* oraw, float* gs, double* bstats,
-                      cudaStream_t st);
-int launch_bwd_proj(const Dims& m, const MtAxialParams& p, const MtAxialGrads& gr, const float* x, const double* stats,
-                    const double* bstats, const float* yraw, const float* dyh, cudaStream_t st);
+int launch_bwd_gather(const Dims& m, const MtAxialParams& p, const float* dout, const float* oraw, float* gs,
+                      const double* stats, double* bstats, float* bcoef, unsigned* bcnt, cudaStream_t st);
+int launch_bwd_proj(const Dims& m, const MtAxialParams& p, const MtAxialGrads& gr, const float* x, const float* bcoef,
+                    const float* yraw, const float* dyh, cudaStream_t st);
 static int pow2_le(int x) { int p = 1; while (p * 2 <= x) p *= 2; return p; }
 
 template <typename K>
@@ -383,17 +370,20 @@ int axial_backward_launch(const Dims& m, const MtAxialParams& p, const float* x,
   const float* oraw = reinterpret_cast<const float*>(saved + m.sv_oraw);
   const float* lse = reinterpret_cast<const float*>(saved + m.sv_lse);
   double* bstats = reinterpret_cast<double*>(ws + m.ws_bstats);
+  unsigned* bcnt = reinterpret_cast<unsigned*>(ws + m.ws_cnt);
+  float* bcoef = reinterpret_cast<float*>(ws + m.ws_coef);
+  const float* coef = reinterpret_cast<const float*>(saved + m.sv_coef);
   float* gs = reinterpret_cast<float*>(ws + m.ws_gs);
   float* dyh = reinterpret_cast<float*>(ws + m.ws_dyh);
   int nl = 0;
   if (mask == 0x1f) {
-  if (cudaMemsetAsync(bstats, 0, sizeof(double) * (size_t)MT_NREP * m.ngroups * m.nstat_b, st) != cudaSuccess) return -1;
+  if (cudaMemsetAsync(ws + m.ws_bstats, 0, m.ws_zero_bytes, st) != cudaSuccess) return -1;
   if (gr.dw_qkv && cudaMemsetAsync(gr.dw_qkv, 0, sizeof(float) * 2 * (size_t)m.C * m.C, st) != cudaSuccess) return -1;
   if (m.pos && gr.drelative &&
       cudaMemsetAsync(gr.drelative, 0, sizeof(float) * 2 * (size_t)m.gp * (2 * m.L - 1), st) != cudaSuccess)
     return -1;
   }
-  if (mask & 1) nl += launch_bwd_gather(m, dout, oraw, gs, bstats, st);
+  if (mask & 1) nl += launch_bwd_gather(m, p, dout, oraw, gs, stats, bstats, bcoef, bcnt, st);
   int spb = 1;
   while (spb * MT_G * m.L < 256 && spb * 2 <= m.Bg && m.Bg % (spb * 2) == 0) spb *= 2;
   const bool p2 = (m.L & (m.L - 1)) == 0;
@@ -404,7 +394,7 @@ int axial_backward_launch(const Dims& m, const MtAxialParams& p, const float* x,
     if (smem > 227 * 1024) return -2;
 #define CALL_BS(DD, PP)                                                                               \
     if (set_smem_b(k_bwd_simstats<DD, PP>, smem) != cudaSuccess) return -1;                             \
-    k_bwd_simstats<DD, PP><<<m.B / spb, 256, smem, st>>>(m, p, stats, bstats, yraw, oraw, lse, gs, spb, segw)
+    k_bwd_simstats<DD, PP><<<m.B / spb, 256, smem, st>>>(m, p, stats, bstats, coef, bcoef, bcnt, yraw, oraw, lse, gs, spb, segw)
     MT_DISPATCH_DB(m, CALL_BS)
 #undef CALL_BS
     ++nl;
@@ -417,13 +407,13 @@ int axial_backward_launch(const Dims& m, const MtAxialParams& p, const float* x,
     if (m.pos && !gr.drelative) return -3;
 #define CALL_BA(DD, PP)                                                                               \
     if (set_smem_b(k_bwd_attn<DD, PP>, smem) != cudaSuccess) return -1;                                 \
-    k_bwd_attn<DD, PP><<<m.B / spb, 256, smem, st>>>(m, p, stats, bstats, yraw, oraw, lse, gs, dyh,     \
-                                                     gr.drelative, spb, segw)
+    k_bwd_attn<DD, PP><<<m.B / spb, 256, smem, st>>>(m, p, gr, stats, bstats, coef, bcoef, bcnt, yraw, oraw, lse, \
+                                                     gs, dyh, gr.drelative, spb, segw)
     MT_DISPATCH_DB(m, CALL_BA)
 #undef CALL_BA
     ++nl;
   }
-  if (mask & 8) nl += launch_bwd_proj(m, p, gr, x, stats, bstats, yraw, dyh, st);
+  if (mask & 8) nl += launch_bwd_proj(m, p, gr, x, bcoef, yraw, dyh, st);
   *nlaunch = nl;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -13,16 +13,10 @@
 #include "common.cuh"
 
 // ============================================================================ shared loaders
-// qkv BN coefficients (y_hat = a*y_raw + b) for all 2C channels of statistic group `grp`
-__device__ __forceinline__ void load_qkv_coef(const Dims& m, const MtAxialParams& p, const double* stats, int grp,
-                                              float* ca, float* cb) {
-  const double n = (double)m.Bg * m.L;
-  for (int ch = threadIdx.x; ch < 2 * m.C; ch += blockDim.x) {
-    BnCoef c = bn_coef(m.training, m.training ? stat_get(m, stats, grp, m.nstat_f, m.f_qkv_sum + ch) : 0.0,
-                       m.training ? stat_get(m, stats, grp, m.nstat_f, m.f_qkv_sq + ch) : 0.0, n,
-                       1.f, p.bn_qkv_w[ch], p.bn_qkv_b[ch], p.bn_qkv_rm[ch], p.bn_qkv_rv[ch], m.eps);
-    ca[ch] = c.a; cb[ch] = c.b;
-  }
+// qkv BN coefficients (y_hat = a*y_raw + b) of statistic group `grp`, from the table k_proj's last CTA wrote
+__device__ __forceinline__ void load_qkv_coef(const Dims& m, const float* __restrict__ coef, int grp, float* ca, float* cb) {
+  const float* tb = coef + (size_t)grp * m.ncoef_f + m.cf_q;
+  for (int ch = threadIdx.x; ch < 2 * m.C; ch += blockDim.x) { ca[ch] = tb[2 * ch]; cb[ch] = tb[2 * ch + 1]; }
 }
 
 // normalised q,k,v strips of `spb` consecutive strips starting at b0 -> Yn[s][ch][LP]
@@ -42,23 +36,11 @@ __device__ __forceinline__ void load_rel(const Dims& m, const float* __restrict_
   for (int idx = threadIdx.x; idx < nrel; idx += blockDim.x) R[idx] = __ldg(rel + idx);
 }
 
-__device__ __forceinline__ float gate_of(const float* p) { return p ? __ldg(p) : 1.f; }
-
-// softmax-side weight of similarity term t, head g:  a_t = gamma*f/sqrt(f^2 var + eps)
-__device__ __forceinline__ BnCoef sim_coef(const Dims& m, const MtAxialParams& p, const double* stats, int grp, int t,
-                                           int g) {
-  const int ch = t * MT_G + g;
-  const float f = t == 0 ? 1.f : (t == 1 ? gate_of(p.f_qr) : gate_of(p.f_kr));
-  const double n = (double)m.Bg * m.L * m.L;
-  return bn_coef(m.training, m.training ? stat_get(m, stats, grp, m.nstat_f, m.f_sim_sum + ch) : 0.0,
-                 m.training ? stat_get(m, stats, grp, m.nstat_f, m.f_sim_sq + ch) : 0.0, n, f,
-                 p.bn_sim_w[ch], p.bn_sim_b[ch], p.bn_sim_rm[ch], p.bn_sim_rv[ch], m.eps);
-}
-
 // ============================================================================ k_sim_stats
 template <int D, bool POS>
 __global__ void __launch_bounds__(256)
-k_sim_stats(Dims m, MtAxialParams p, const float* __restrict__ yraw, double* __restrict__ stats, int SPB, int segw) {
+k_sim_stats(Dims m, MtAxialParams p, const float* __restrict__ yraw, double* __restrict__ stats,
+            float* __restrict__ coef, unsigned* __restrict__ cnt, int SPB, int segw) {
   extern __shared__ float sm[];
   const int C = m.C, L = m.L, LP = m.LP, RL = 2 * L - 1;
   float* ca = sm;
@@ -68,7 +50,7 @@ k_sim_stats(Dims m, MtAxialParams p, const float* __restrict__ yraw, double* __r
   float* R = Yn + (size_t)SPB * 2 * C * LP;
   const int b0 = blockIdx.x * SPB;
   const int grp = b0 / m.Bg;
-  load_qkv_coef(m, p, stats, grp, ca, cb);
+  load_qkv_coef(m, coef, grp, ca, cb);
   if (threadIdx.x < 48) red[threadIdx.x] = 0.f;
   if (POS) load_rel(m, p.relative, R);
   __syncthreads();
@@ -117,19 +99,14 @@ k_sim_stats(Dims m, MtAxialParams p, const float* __restrict__ yraw, double* __r
     MT_GADD(m, st + m.f_sim_sum + threadIdx.x, (double)red[threadIdx.x * 2 + 0]);
     MT_GADD(m, st + m.f_sim_sq + threadIdx.x, (double)red[threadIdx.x * 2 + 1]);
   }
-  // running statistics of bn_qkv: one CTA, sequential EMA over the statistic groups
-  if (blockIdx.x == 0) {
-    const double n = (double)m.Bg * L;
-    for (int ch = threadIdx.x; ch < 2 * C; ch += blockDim.x)
-      ema_update(m, p.bn_qkv_rm, p.bn_qkv_rv, ch, stats, m.nstat_f, m.f_qkv_sum, m.f_qkv_sq, n, 1.f);
-  }
+  if (last_cta_done(cnt + 1, gridDim.x)) fin_sim(m, p, stats, coef);   // softmax weights + bn_similarity running stats
 }
 
 // ============================================================================ k_attn
 template <int D, bool POS>
 __global__ void __launch_bounds__(256)
-k_attn(Dims m, MtAxialParams p, const float* __restrict__ yraw, double* __restrict__ stats, float* __restrict__ oraw,
-       float* __restrict__ lse, int SPB, int segw) {
+k_attn(Dims m, MtAxialParams p, const float* __restrict__ yraw, double* __restrict__ stats, float* __restrict__ coef,
+       unsigned* __restrict__ cnt, float* __restrict__ oraw, float* __restrict__ lse, int SPB, int segw) {
   constexpr int GP = 2 * D;
   extern __shared__ float sm[];
   const int C = m.C, L = m.L, LP = m.LP, RL = 2 * L - 1;
@@ -142,11 +119,8 @@ k_attn(Dims m, MtAxialParams p, const float* __restrict__ yraw, double* __restri
   float* R = Yn + (size_t)SPB * 2 * C * LP;
   const int b0 = blockIdx.x * SPB;
   const int grp = b0 / m.Bg;
-  load_qkv_coef(m, p, stats, grp, ca, cb);
-  if (threadIdx.x < m.nt * MT_G) {
-    BnCoef c = sim_coef(m, p, stats, grp, threadIdx.x / MT_G, threadIdx.x % MT_G);
-    wsim[threadIdx.x] = c.a * MT_LOG2E;
-  }
+  load_qkv_coef(m, coef, grp, ca, cb);
+  if (threadIdx.x < m.nt * MT_G) wsim[threadIdx.x] = coef[(size_t)grp * m.ncoef_f + m.cf_s + 2 * threadIdx.x];
   for (int k = threadIdx.x; k < 2 * NO * C; k += blockDim.x) red[k] = 0.f;
   if (POS) load_rel(m, p.relative, R);
   __syncthreads();
@@ -226,21 +200,14 @@ k_attn(Dims m, MtAxialParams p, const float* __restrict__ yraw, double* __restri
       MT_GADD(m, st + m.f_out_sum + ch, (double)red[ch * 2]);
       MT_GADD(m, st + m.f_out_sq + ch, (double)red[ch * 2 + 1]);
     }
-    if (blockIdx.x == 0) {                 // running statistics of bn_similarity
-      const double n = (double)m.Bg * L * L;
-      for (int ch = threadIdx.x; ch < m.nt * MT_G; ch += blockDim.x) {
-        const int t = ch / MT_G;
-        const float f = t == 0 ? 1.f : (t == 1 ? gate_of(p.f_qr) : gate_of(p.f_kr));
-        ema_update(m, p.bn_sim_rm, p.bn_sim_rv, ch, stats, m.nstat_f, m.f_sim_sum, m.f_sim_sq, n, f);
-      }
-    }
   }
+  if (last_cta_done(cnt + 2, gridDim.x)) fin_out(m, p, stats, coef);      // bn_output coefficients + running stats
 }
 
 // ============================================================================ host launchers
-int launch_proj(const Dims& m, const float* x, const float* w, float* yraw, double* stats, cudaStream_t st);
-int launch_out(const Dims& m, const MtAxialParams& p, const double* stats, const float* oraw, float* out,
-               cudaStream_t st);
+int launch_proj(const Dims& m, const MtAxialParams& p, const float* x, float* yraw, double* stats, float* coef,
+                unsigned* cnt, cudaStream_t st);
+int launch_out(const Dims& m, const float* coef, const float* oraw, float* out, cudaStream_t st);
 
 struct LaunchPlan { int SPB, segw; size_t smem_attn; };
 
@@ -279,20 +246,22 @@ static cudaError_t set_smem(K kern, size_t bytes) {
 int axial_forward_launch(const Dims& m, const MtAxialParams& p, const float* x, float* out, char* saved,
                          cudaStream_t st, int* nlaunch, int mask) {
   double* stats = reinterpret_cast<double*>(saved + m.sv_stats);
+  unsigned* cnt = reinterpret_cast<unsigned*>(saved + m.sv_cnt);
+  float* coef = reinterpret_cast<float*>(saved + m.sv_coef);
   float* yraw = reinterpret_cast<float*>(saved + m.sv_yraw);
   float* oraw = reinterpret_cast<float*>(saved + m.sv_oraw);
   float* lse = reinterpret_cast<float*>(saved + m.sv_lse);
   int nl = 0;
-  if (m.training && mask == 0x1f) {
-    if (cudaMemsetAsync(stats, 0, sizeof(double) * (size_t)MT_NREP * m.ngroups * m.nstat_f, st) != cudaSuccess) return -1;
+  if (mask == 0x1f) {      // accumulators + CTA-done tickets
+    if (cudaMemsetAsync(saved + m.sv_stats, 0, m.sv_zero_bytes, st) != cudaSuccess) return -1;
   }
-  if (mask & 1) nl += launch_proj(m, x, p.w_qkv, yraw, stats, st);
+  if (mask & 1) nl += launch_proj(m, p, x, yraw, stats, coef, cnt, st);
   if (m.training && (mask & 2)) {
     LaunchPlan pl = plan_attn(m, 0, 48);
     if (pl.smem_attn > 227 * 1024) return -2;
 #define CALL_SIM(DD, PP)                                                                       \
     if (set_smem(k_sim_stats<DD, PP>, pl.smem_attn) != cudaSuccess) return -1;                   \
-    k_sim_stats<DD, PP><<<m.B / pl.SPB, 256, pl.smem_attn, st>>>(m, p, yraw, stats, pl.SPB, pl.segw)
+    k_sim_stats<DD, PP><<<m.B / pl.SPB, 256, pl.smem_attn, st>>>(m, p, yraw, stats, coef, cnt, pl.SPB, pl.segw)
     MT_DISPATCH_D(m, CALL_SIM)
 #undef CALL_SIM
     ++nl;
@@ -302,12 +271,12 @@ int axial_forward_launch(const Dims& m, const MtAxialParams& p, const float* x, 
     if (pl.smem_attn > 227 * 1024) return -2;
 #define CALL_ATTN(DD, PP)                                                                      \
     if (set_smem(k_attn<DD, PP>, pl.smem_attn) != cudaSuccess) return -1;                        \
-    k_attn<DD, PP><<<m.B / pl.SPB, 256, pl.smem_attn, st>>>(m, p, yraw, stats, oraw, lse, pl.SPB, pl.segw)
+    k_attn<DD, PP><<<m.B / pl.SPB, 256, pl.smem_attn, st>>>(m, p, yraw, stats, coef, cnt, oraw, lse, pl.SPB, pl.segw)
     MT_DISPATCH_D(m, CALL_ATTN)
 #undef CALL_ATTN
     ++nl;
   }
-  if (mask & 8) nl += launch_out(m, p, stats, oraw, out, st);
+  if (mask & 8) nl += launch_out(m, coef, oraw, out, st);
   *nlaunch = nl;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

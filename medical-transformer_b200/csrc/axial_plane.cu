@@ -7,28 +7,10 @@
 // other case is one element per thread.
 #include "common.cuh"
 
-__device__ __forceinline__ float gate_pl(const float* p) { return p ? __ldg(p) : 1.f; }
-
-__device__ __forceinline__ BnCoef out_coef(const Dims& m, const MtAxialParams& p, const double* stats, int grp, int ch) {
-  const float f = (m.no == 2 && (ch & 1)) ? gate_pl(p.f_sve) : gate_pl(p.f_sv);
-  return bn_coef(m.training, m.training ? stat_get(m, stats, grp, m.nstat_f, m.f_out_sum + ch) : 0.0,
-                 m.training ? stat_get(m, stats, grp, m.nstat_f, m.f_out_sq + ch) : 0.0, (double)m.Bg * m.L, f,
-                 p.bn_out_w[ch], p.bn_out_b[ch], p.bn_out_rm[ch], p.bn_out_rv[ch], m.eps);
-}
-
-__device__ __forceinline__ void out_running_stats(const Dims& m, const MtAxialParams& p, const double* stats) {
-  const double cnt = (double)m.Bg * m.L;
-  for (int ch = threadIdx.x; ch < m.no * m.C; ch += blockDim.x) {
-    const float f = (m.no == 2 && (ch & 1)) ? gate_pl(p.f_sve) : gate_pl(p.f_sv);
-    ema_update(m, p.bn_out_rm, p.bn_out_rv, ch, stats, m.nstat_f, m.f_out_sum, m.f_out_sq, cnt, f);
-  }
-}
-
 // ---------------------------------------------------------------------------- k_out_direct
 // one output element per thread; a CTA covers 256 consecutive NCHW outputs
 __global__ void __launch_bounds__(256)
-k_out_direct(Dims m, MtAxialParams p, const double* __restrict__ stats, const float* __restrict__ oraw,
-             float* __restrict__ out) {
+k_out_direct(Dims m, const float* __restrict__ coef, const float* __restrict__ oraw, float* __restrict__ out) {
   __shared__ float sa[512], sb[512];
   const int NO = m.no, L = m.L, st_ = m.stride, Ho = m.H / st_, Wo = m.W / st_, HW = Ho * Wo;
   const long total = (long)m.N * m.C * HW;
@@ -39,8 +21,8 @@ k_out_direct(Dims m, MtAxialParams p, const double* __restrict__ stats, const fl
   for (int k = threadIdx.x; k < nplanes * NO; k += 256) {
     const int plane = plane0 + k / NO, s = k % NO;
     const int n = plane / m.C, c = plane - n * m.C;
-    BnCoef kf = out_coef(m, p, stats, n / (m.N / m.ngroups), c * NO + s);
-    sa[k] = kf.a; sb[k] = kf.b;
+    const float* tb = coef + (size_t)(n / (m.N / m.ngroups)) * m.ncoef_f + m.cf_o + 2 * (c * NO + s);
+    sa[k] = tb[0]; sb[k] = tb[1];
   }
   __syncthreads();
   const long idx = first + threadIdx.x;
@@ -62,22 +44,20 @@ k_out_direct(Dims m, MtAxialParams p, const double* __restrict__ stats, const fl
       }
     out[idx] = fmaf(acc, 1.f / (float)(st_ * st_), bsum);
   }
-  if (m.training && blockIdx.x == 0) out_running_stats(m, p, stats);
 }
 
 // ---------------------------------------------------------------------------- k_out_t
 // axis 0, stride 1: 32(h) x 32(w) tile of one (n, c) plane through smem
 __global__ void __launch_bounds__(256)
-k_out_t(Dims m, MtAxialParams p, const double* __restrict__ stats, const float* __restrict__ oraw,
-        float* __restrict__ out) {
+k_out_t(Dims m, const float* __restrict__ coef, const float* __restrict__ oraw, float* __restrict__ out) {
   __shared__ float tile[32][33];
   __shared__ float sa[2], sb[2];
   const int NO = m.no, L = m.L;
   const int n = blockIdx.z / m.C, c = blockIdx.z - n * m.C;
   const int w0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
   if (threadIdx.x < NO) {
-    BnCoef kf = out_coef(m, p, stats, n / (m.N / m.ngroups), c * NO + threadIdx.x);
-    sa[threadIdx.x] = kf.a; sb[threadIdx.x] = kf.b;
+    const float* tb = coef + (size_t)(n / (m.N / m.ngroups)) * m.ncoef_f + m.cf_o + 2 * (c * NO + threadIdx.x);
+    sa[threadIdx.x] = tb[0]; sb[threadIdx.x] = tb[1];
   }
   __syncthreads();
   const float a0 = sa[0], a1 = NO == 2 ? sa[1] : 0.f, bsum = sb[0] + (NO == 2 ? sb[1] : 0.f);
@@ -99,12 +79,12 @@ k_out_t(Dims m, MtAxialParams p, const double* __restrict__ stats, const float* 
     const int hl = ty + 8 * rr, h = h0 + hl, w = w0 + tx;
     if (h < m.H && w < m.W) out[((size_t)blockIdx.z * m.H + h) * m.W + w] = tile[tx][hl] + bsum;
   }
-  if (m.training && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) out_running_stats(m, p, stats);
 }
 
 // ---------------------------------------------------------------------------- backward gather
-__device__ __forceinline__ void gather_reduce(const Dims& m, float s1, float s2a, float s2b, int c, int grp,
-                                              double* bstats, int cta) {
+__device__ __forceinline__ void gather_reduce(const Dims& m, const MtAxialParams& p, float s1, float s2a, float s2b,
+                                              int c, int grp, const double* stats, double* bstats, float* bcoef,
+                                              unsigned* bcnt, int cta) {
   __shared__ float red[3][8];
   s1 = seg_sum(s1, 32); s2a = seg_sum(s2a, 32); s2b = seg_sum(s2b, 32);
   const int wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
@@ -118,12 +98,14 @@ __device__ __forceinline__ void gather_reduce(const Dims& m, float s1, float s2a
     else if (threadIdx.x == 1) MT_GADD(m, bs + m.b_out_s2 + c * m.no, (double)t);
     else if (m.no == 2) MT_GADD(m, bs + m.b_out_s2 + c * m.no + 1, (double)t);
   }
+  if (last_cta_done(bcnt + 0, gridDim.x * gridDim.y * gridDim.z)) fin_bwd_out(m, p, stats, bstats, bcoef);
 }
 
 // grid (ceil(H*W / blockDim), N*C): one full-resolution position per thread
 __global__ void __launch_bounds__(256)
-k_bwd_gather_direct(Dims m, const float* __restrict__ dout, const float* __restrict__ oraw, float* __restrict__ gs,
-                    double* __restrict__ bstats) {
+k_bwd_gather_direct(Dims m, MtAxialParams p, const float* __restrict__ dout, const float* __restrict__ oraw,
+                    float* __restrict__ gs, const double* __restrict__ stats, double* __restrict__ bstats,
+                    float* __restrict__ bcoef, unsigned* __restrict__ bcnt) {
   const int plane = blockIdx.y, n = plane / m.C, c = plane - n * m.C;
   const int NO = m.no, L = m.L, st_ = m.stride, Ho = m.H / st_, Wo = m.W / st_;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -138,13 +120,14 @@ k_bwd_gather_direct(Dims m, const float* __restrict__ dout, const float* __restr
     s1 = g; s2a = g * __ldg(o);
     if (NO == 2) s2b = g * __ldg(o + L);
   }
-  gather_reduce(m, s1, s2a, s2b, c, n / (m.N / m.ngroups), bstats, blockIdx.x + blockIdx.y);
+  gather_reduce(m, p, s1, s2a, s2b, c, n / (m.N / m.ngroups), stats, bstats, bcoef, bcnt, blockIdx.x + blockIdx.y);
 }
 
 // axis 0, stride 1: 32x32 tile transpose.  grid (ceil(W/32), ceil(H/32), N*C)
 __global__ void __launch_bounds__(256)
-k_bwd_gather_t(Dims m, const float* __restrict__ dout, const float* __restrict__ oraw, float* __restrict__ gs,
-               double* __restrict__ bstats) {
+k_bwd_gather_t(Dims m, MtAxialParams p, const float* __restrict__ dout, const float* __restrict__ oraw,
+               float* __restrict__ gs, const double* __restrict__ stats, double* __restrict__ bstats,
+               float* __restrict__ bcoef, unsigned* __restrict__ bcnt) {
   __shared__ float tile[32][33];
   const int NO = m.no, L = m.L;
   const int n = blockIdx.z / m.C, c = blockIdx.z - n * m.C;
@@ -169,32 +152,31 @@ k_bwd_gather_t(Dims m, const float* __restrict__ dout, const float* __restrict__
       if (NO == 2) s2b = fmaf(g, __ldg(o + L), s2b);
     }
   }
-  gather_reduce(m, s1, s2a, s2b, c, n / (m.N / m.ngroups), bstats, blockIdx.x + blockIdx.y + blockIdx.z);
+  gather_reduce(m, p, s1, s2a, s2b, c, n / (m.N / m.ngroups), stats, bstats, bcoef, bcnt, blockIdx.x + blockIdx.y + blockIdx.z);
 }
 
 // ---------------------------------------------------------------------------- host launchers
-int launch_out(const Dims& m, const MtAxialParams& p, const double* stats, const float* oraw, float* out,
-               cudaStream_t st) {
+int launch_out(const Dims& m, const float* coef, const float* oraw, float* out, cudaStream_t st) {
   if (m.axis == 0 && m.stride == 1) {
     dim3 grid((m.W + 31) / 32, (m.H + 31) / 32, m.N * m.C);
-    k_out_t<<<grid, 256, 0, st>>>(m, p, stats, oraw, out);
+    k_out_t<<<grid, 256, 0, st>>>(m, coef, oraw, out);
   } else {
     const long total = (long)m.N * m.C * (m.H / m.stride) * (m.W / m.stride);
-    k_out_direct<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(m, p, stats, oraw, out);
+    k_out_direct<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(m, coef, oraw, out);
   }
   return 1;
 }
 
-int launch_bwd_gather(const Dims& m, const float* dout, const float* oraw, float* gs, double* bstats,
-                      cudaStream_t st) {
+int launch_bwd_gather(const Dims& m, const MtAxialParams& p, const float* dout, const float* oraw, float* gs,
+                      const double* stats, double* bstats, float* bcoef, unsigned* bcnt, cudaStream_t st) {
   if (m.axis == 0 && m.stride == 1) {
     dim3 grid((m.W + 31) / 32, (m.H + 31) / 32, m.N * m.C);
-    k_bwd_gather_t<<<grid, 256, 0, st>>>(m, dout, oraw, gs, bstats);
+    k_bwd_gather_t<<<grid, 256, 0, st>>>(m, p, dout, oraw, gs, stats, bstats, bcoef, bcnt);
   } else {
     const int hw = m.H * m.W;
     int bs = hw >= 256 ? 256 : ((hw + 31) / 32) * 32;
     dim3 grid((hw + bs - 1) / bs, m.N * m.C);
-    k_bwd_gather_direct<<<grid, bs, 0, st>>>(m, dout, oraw, gs, bstats);
+    k_bwd_gather_direct<<<grid, bs, 0, st>>>(m, p, dout, oraw, gs, stats, bstats, bcoef, bcnt);
   }
   return 1;
 }

@@ -55,8 +55,9 @@ __device__ __forceinline__ void mma_chunk(const float* As, const float* Bs, int 
 // ============================================================================ k_proj
 // grid (position tiles, ceil(2C/64)).  M = oc (ty), N = position (tx).
 __global__ void __launch_bounds__(256)
-k_proj(Dims m, const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ yraw,
-       double* __restrict__ stats, int TS, int TL, int tiles_per_group, int nTL) {
+k_proj(Dims m, MtAxialParams p, const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ yraw,
+       double* __restrict__ stats, float* __restrict__ coef, unsigned* __restrict__ cnt, int TS, int TL,
+       int tiles_per_group, int nTL) {
   __shared__ __align__(16) float As[16 * TILE_LD];
   __shared__ __align__(16) float Bs[16 * TILE_LD];
   __shared__ float red[64][2];
@@ -124,18 +125,19 @@ k_proj(Dims m, const float* __restrict__ x, const float* __restrict__ w, float* 
       MT_GADD(m, st + m.f_qkv_sq + oc0 + tid, (double)red[tid][1]);
     }
   }
+  // last CTA: bn_qkv coefficients (+ running stats); in eval mode also the similarity weights,
+  // because k_sim_stats is not launched then
+  if (last_cta_done(cnt + 0, gridDim.x * gridDim.y)) {
+    fin_qkv(m, p, stats, coef);
+    if (!m.training) fin_sim(m, p, stats, coef);
+  }
 }
 
 // ============================================================================ k_bwd_dx
 // grid (position tiles, ceil(C/64)).  M = c (ty), N = position (tx), K = 2C.
-// CTA (0,0) also emits every BN-parameter / gate gradient from the fp64 sums.
-__device__ void bwd_param_grads(const Dims& m, const MtAxialParams& p, const MtAxialGrads& gr,
-                                const double* stats, const double* bstats);
-
 __global__ void __launch_bounds__(256)
-k_bwd_dx(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stats,
-         const double* __restrict__ bstats, const float* __restrict__ yraw, const float* __restrict__ dyh,
-         int TS, int TL, int tiles_per_group, int nTL) {
+k_bwd_dx(Dims m, MtAxialParams p, MtAxialGrads gr, const float* __restrict__ bcoef,
+         const float* __restrict__ yraw, const float* __restrict__ dyh, int TS, int TL, int tiles_per_group, int nTL) {
   extern __shared__ __align__(16) float smx[];
   float* As = smx;                          // [16][TILE_LD]
   float* Bs = As + 16 * TILE_LD;            // [16][TILE_LD]
@@ -147,14 +149,9 @@ k_bwd_dx(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ st
   const int C = m.C, K = 2 * C;
   const PosTile t = pos_tile(m, blockIdx.x, TS, TL, tiles_per_group, nTL);
   const int c0 = blockIdx.y * 64;
-  for (int ch = tid; ch < K; ch += 256) {
-    const double n = (double)m.Bg * m.L;
-    BnBwdCoef k = bn_bwd_coef(m.training, m.training ? stat_get(m, stats, t.grp, m.nstat_f, m.f_qkv_sum + ch) : 0.0,
-                              m.training ? stat_get(m, stats, t.grp, m.nstat_f, m.f_qkv_sq + ch) : 0.0, n, 1.f,
-                              p.bn_qkv_w[ch], p.bn_qkv_rv[ch], m.eps,
-                              m.training ? stat_get(m, bstats, t.grp, m.nstat_b, m.b_qkv_s1 + ch) : 0.0,
-                              m.training ? stat_get(m, bstats, t.grp, m.nstat_b, m.b_qkv_s2 + ch) : 0.0);
-    qA[ch] = k.A; qB[ch] = k.Bc; qC[ch] = k.Cc;
+  {
+    const float* tb = bcoef + (size_t)t.grp * m.ncoef_b + m.cb_q;
+    for (int ch = tid; ch < K; ch += 256) { qA[ch] = tb[3 * ch]; qB[ch] = tb[3 * ch + 1]; qC[ch] = tb[3 * ch + 2]; }
   }
   __syncthreads();
   float acc[4][4];
@@ -203,15 +200,14 @@ k_bwd_dx(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ st
         gr.dx[nchw_addr(m, t.grp * m.Bg + t.sb0 + s, c0 + cc, t.l0 + l)] = Ts[cc * 65 + s * t.TL + l];
     }
   }
-  if (blockIdx.x == 0 && blockIdx.y == 0) bwd_param_grads(m, p, gr, stats, bstats);
 }
 
 // ============================================================================ k_bwd_dw
 // grid (ceil(2C/64), ceil(C/64), KSPLIT).  M = oc (ty), N = c (tx), K = positions of this split.
 __global__ void __launch_bounds__(256)
-k_bwd_dw(Dims m, MtAxialParams p, MtAxialGrads gr, const float* __restrict__ x, const double* __restrict__ stats,
-         const double* __restrict__ bstats, const float* __restrict__ yraw, const float* __restrict__ dyh,
-         int TS, int TL, int tiles_per_group, int nTL, int ntiles) {
+k_bwd_dw(Dims m, MtAxialGrads gr, const float* __restrict__ x, const float* __restrict__ bcoef,
+         const float* __restrict__ yraw, const float* __restrict__ dyh, int TS, int TL, int tiles_per_group, int nTL,
+         int ntiles) {
   extern __shared__ __align__(16) float smw[];
   float* Am = smw;                          // [64 pos][TILE_LD]  (k-major: As[k][m] with k = pos)
   float* Bm = Am + 64 * TILE_LD;            // [64 pos][TILE_LD]
@@ -231,14 +227,9 @@ k_bwd_dw(Dims m, MtAxialParams p, MtAxialGrads gr, const float* __restrict__ x, 
     const PosTile t = pos_tile(m, tile, TS, TL, tiles_per_group, nTL);
     if (t.grp != cur_grp) {                 // bn_qkv backward coefficients of this statistic group
       __syncthreads();
-      for (int ch = tid; ch < M; ch += 256) {
-        const double n = (double)m.Bg * m.L;
-        BnBwdCoef k = bn_bwd_coef(m.training, m.training ? stat_get(m, stats, t.grp, m.nstat_f, m.f_qkv_sum + ch) : 0.0,
-                                  m.training ? stat_get(m, stats, t.grp, m.nstat_f, m.f_qkv_sq + ch) : 0.0, n, 1.f,
-                                  p.bn_qkv_w[ch], p.bn_qkv_rv[ch], m.eps,
-                                  m.training ? stat_get(m, bstats, t.grp, m.nstat_b, m.b_qkv_s1 + ch) : 0.0,
-                                  m.training ? stat_get(m, bstats, t.grp, m.nstat_b, m.b_qkv_s2 + ch) : 0.0);
-        qA[ch] = k.A; qB[ch] = k.Bc; qC[ch] = k.Cc;
+      {
+        const float* tb = bcoef + (size_t)t.grp * m.ncoef_b + m.cb_q;
+        for (int ch = tid; ch < M; ch += 256) { qA[ch] = tb[3 * ch]; qB[ch] = tb[3 * ch + 1]; qC[ch] = tb[3 * ch + 2]; }
       }
       cur_grp = t.grp;
       __syncthreads();
@@ -280,89 +271,6 @@ k_bwd_dw(Dims m, MtAxialParams p, MtAxialGrads gr, const float* __restrict__ x, 
   }
 }
 
-// ============================================================================ parameter gradients
-__device__ __forceinline__ float gate_p(const float* p) { return p ? __ldg(p) : 1.f; }
-
-__device__ void bwd_param_grads(const Dims& m, const MtAxialParams& p, const MtAxialGrads& gr,
-                                const double* stats, const double* bstats) {
-  const int tid = threadIdx.x, C = m.C, NO = m.no, NOC = NO * C, NT = m.nt;
-  for (int ch = tid; ch < 2 * C; ch += 256) {
-    double dg = 0.0, db = 0.0;
-    for (int g = 0; g < m.ngroups; ++g) {
-      const double n = (double)m.Bg * m.L;
-      const double s1 = stat_get(m, bstats, g, m.nstat_b, m.b_qkv_s1 + ch), s2 = stat_get(m, bstats, g, m.nstat_b, m.b_qkv_s2 + ch);
-      if (m.training) {
-        double mu = stat_get(m, stats, g, m.nstat_f, m.f_qkv_sum + ch) / n;
-        double var = stat_get(m, stats, g, m.nstat_f, m.f_qkv_sq + ch) / n - mu * mu;
-        if (var < 0.0) var = 0.0;
-        dg += (s2 - mu * s1) / sqrt(var + (double)m.eps);
-      } else {
-        dg += (s2 - (double)p.bn_qkv_rm[ch] * s1) / sqrt((double)p.bn_qkv_rv[ch] + (double)m.eps);
-      }
-      db += s1;
-    }
-    if (gr.dbn_qkv_w) gr.dbn_qkv_w[ch] = (float)dg;
-    if (gr.dbn_qkv_b) gr.dbn_qkv_b[ch] = (float)db;
-  }
-  double gpart[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int ch = tid; ch < NOC; ch += 256) {
-    const int sidx = NO == 2 ? (ch & 1) : 0;
-    const float f = sidx ? gate_p(p.f_sve) : gate_p(p.f_sv);
-    const double gam = p.bn_out_w[ch];
-    double dg = 0.0, db = 0.0;
-    for (int g = 0; g < m.ngroups; ++g) {
-      const double n = (double)m.Bg * m.L;
-      const double s1 = stat_get(m, bstats, g, m.nstat_b, m.b_out_s1 + ch / NO), s2 = stat_get(m, bstats, g, m.nstat_b, m.b_out_s2 + ch);
-      if (m.training) {
-        double mu = stat_get(m, stats, g, m.nstat_f, m.f_out_sum + ch) / n;
-        double var = stat_get(m, stats, g, m.nstat_f, m.f_out_sq + ch) / n - mu * mu;
-        if (var < 0.0) var = 0.0;
-        const double su2 = (double)f * f * var + (double)m.eps, su = sqrt(su2);
-        dg += (double)f * (s2 - mu * s1) / su;
-        gpart[2 + sidx] += gam * (s2 - mu * s1) * (double)m.eps / (su2 * su);
-      } else {
-        const double inv = 1.0 / sqrt((double)p.bn_out_rv[ch] + (double)m.eps);
-        dg += ((double)f * s2 - (double)p.bn_out_rm[ch] * s1) * inv;
-        gpart[2 + sidx] += gam * inv * s2;
-      }
-      db += s1;
-    }
-    if (gr.dbn_out_w) gr.dbn_out_w[ch] = (float)dg;
-    if (gr.dbn_out_b) gr.dbn_out_b[ch] = (float)db;
-  }
-  if (tid < NT * MT_G) {
-    const int ch = tid, t = ch / MT_G;
-    const float f = t == 0 ? 1.f : (t == 1 ? gate_p(p.f_qr) : gate_p(p.f_kr));
-    const double gam = p.bn_sim_w[ch];
-    double dg = 0.0;
-    for (int g = 0; g < m.ngroups; ++g) {
-      const double n = (double)m.Bg * m.L * m.L, T = stat_get(m, bstats, g, m.nstat_b, m.b_sim_t + ch);
-      if (m.training) {
-        double mu = stat_get(m, stats, g, m.nstat_f, m.f_sim_sum + ch) / n;
-        double var = stat_get(m, stats, g, m.nstat_f, m.f_sim_sq + ch) / n - mu * mu;
-        if (var < 0.0) var = 0.0;
-        const double su2 = (double)f * f * var + (double)m.eps, su = sqrt(su2);
-        dg += (double)f * T / su;
-        if (t > 0) gpart[t - 1] += gam * T * (double)m.eps / (su2 * su);
-      } else {
-        const double inv = 1.0 / sqrt((double)p.bn_sim_rv[ch] + (double)m.eps);
-        dg += (double)f * T * inv;
-        if (t > 0) gpart[t - 1] += gam * inv * T;
-      }
-    }
-    if (gr.dbn_sim_w) gr.dbn_sim_w[ch] = (float)dg;
-    if (gr.dbn_sim_b) gr.dbn_sim_b[ch] = 0.f;        // sum dZ == 0: softmax is shift invariant
-  }
-  __shared__ double gred[4][256];                      // fixed-order block reduce -> deterministic
-  for (int k = 0; k < 4; ++k) gred[k][tid] = gpart[k];
-  __syncthreads();
-  if (tid < 4 && gr.dgates) {
-    double t = 0.0;
-    for (int k = 0; k < 256; ++k) t += gred[tid][k];
-    gr.dgates[tid] = (float)t;
-  }
-}
-
 // ============================================================================ host launchers
 static void proj_tiling(const Dims& m, int& TS, int& TL, int& nTL, int& nTS) {
   if (m.axis == 1) { TL = m.L < 64 ? m.L : 64; TS = 64 / TL; if (TS > m.Bg) TS = m.Bg; }
@@ -371,30 +279,32 @@ static void proj_tiling(const Dims& m, int& TS, int& TL, int& nTL, int& nTS) {
   nTL = (m.L + TL - 1) / TL; nTS = (m.Bg + TS - 1) / TS;
 }
 
-int launch_proj(const Dims& m, const float* x, const float* w, float* yraw, double* stats, cudaStream_t st) {
+int launch_proj(const Dims& m, const MtAxialParams& p, const float* x, float* yraw, double* stats, float* coef,
+                unsigned* cnt, cudaStream_t st) {
   int TS, TL, nTL, nTS;
   proj_tiling(m, TS, TL, nTL, nTS);
   dim3 grid(m.ngroups * nTS * nTL, (2 * m.C + 63) / 64);
-  k_proj<<<grid, 256, 0, st>>>(m, x, w, yraw, stats, TS, TL, nTS * nTL, nTL);
+  k_proj<<<grid, 256, 0, st>>>(m, p, x, p.w_qkv, yraw, stats, coef, cnt, TS, TL, nTS * nTL, nTL);
   return 1;
 }
 
-int launch_bwd_proj(const Dims& m, const MtAxialParams& p, const MtAxialGrads& gr, const float* x, const double* stats,
-                    const double* bstats, const float* yraw, const float* dyh, cudaStream_t st) {
+int launch_bwd_proj(const Dims& m, const MtAxialParams& p, const MtAxialGrads& gr, const float* x, const float* bcoef,
+                    const float* yraw, const float* dyh, cudaStream_t st) {
   int TS, TL, nTL, nTS;
   proj_tiling(m, TS, TL, nTL, nTS);
   const int ntiles = m.ngroups * nTS * nTL;
   {
     dim3 grid(ntiles, (m.C + 63) / 64);
     const size_t smem = sizeof(float) * (2 * 16 * TILE_LD + 6 * (size_t)m.C + 64 * 65);
-    k_bwd_dx<<<grid, 256, smem, st>>>(m, p, gr, stats, bstats, yraw, dyh, TS, TL, nTS * nTL, nTL);
+    k_bwd_dx<<<grid, 256, smem, st>>>(m, p, gr, bcoef, yraw, dyh, TS, TL, nTS * nTL, nTL);
   }
   {
     int ksplit = ntiles < 32 ? ntiles : 32;
     dim3 grid((2 * m.C + 63) / 64, (m.C + 63) / 64, ksplit);
     const size_t smem = sizeof(float) * (2 * 64 * TILE_LD + 6 * (size_t)m.C);
-    cudaFuncSetAttribute(k_bwd_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_bwd_dw<<<grid, 256, smem, st>>>(m, p, gr, x, stats, bstats, yraw, dyh, TS, TL, nTS * nTL, nTL, ntiles);
+    static bool once = (cudaFuncSetAttribute(k_bwd_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), true);
+    (void)once;
+    k_bwd_dw<<<grid, 256, smem, st>>>(m, gr, x, bcoef, yraw, dyh, TS, TL, nTS * nTL, nTL, ntiles);
   }
   return 2;
 }
