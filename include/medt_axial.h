@@ -9,6 +9,8 @@
  *                         AxialAttention_wopos.forward    axialnet.py:222-253  (variant 2)
  *   mt_axial_backward  <- torch.autograd over the same lines (the reference has no
  *                         hand-written backward; train.py:160 calls loss.backward())
+ *   mt_bn_act_*        <- BatchNorm2d(+ReLU)(+residual) glue of the blocks / stems / LoGo loop
+ *   mt_up2x_relu_add_* <- relu(bilinear x2) + skip of the decoders
  *
  * Conventions
  *   - plain C, no torch types; all pointers are DEVICE pointers unless named host_*;
@@ -102,6 +104,32 @@ int mt_axial_forward(const MtAxialDesc* d, const MtAxialParams* p, const float* 
  * desc / x / params. */
 int mt_axial_backward(const MtAxialDesc* d, const MtAxialParams* p, const float* x, const float* dout,
                       const void* saved, void* workspace, const MtAxialGrads* g, void* stream);
+
+/* ---- fused glue of the conv shell (all NCHW fp32) ---------------------------------------------
+ * relu(F.interpolate(in, scale_factor=2, mode='bilinear', align_corners=False)) + skip
+ *   <- one decoder step, axialnet.py:493-501 / :650-652 / :690-698.
+ * in: (planes, H, W) with planes = N*C; out / skip / mask: (planes, 2H, 2W); skip may be NULL;
+ * mask (1 byte per output, = pre-activation > 0) may be NULL when no backward will follow. */
+int mt_up2x_relu_add_forward(int planes, int H, int W, const float* in, const float* skip, float* out,
+                             unsigned char* mask, void* stream);
+/* din = upsample^T(dout * mask); the gradient of `skip` is dout itself (not written). */
+int mt_up2x_relu_add_backward(int planes, int H, int W, const float* dout, const unsigned char* mask, float* din,
+                              void* stream);
+
+/* y = [relu]( BatchNorm2d(x) [+ residual] ) with batch statistics per statistic group
+ *   <- bn+relu(+identity) of AxialBlock*.forward axialnet.py:285-300 / :327-342 / :373-389, the
+ *      stems :475-483, and the 16 per-patch calls of the LoGo loop :661-700 (groups = 16:
+ *      per-group statistics + `groups` sequential running-stat EMA steps, as 16 BN calls do).
+ * x, residual (nullable), y: (N, C, HW).  save_mean: (2*groups, C) [means, then biased
+ * variances]; save_invstd: (groups, C).  training = 0 uses / leaves the running statistics. */
+int mt_bn_act_forward(int N, int C, int HW, int groups, int training, int relu, float eps, float momentum,
+                      const float* x, const float* residual, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, float* y, float* save_mean, float* save_invstd,
+                      void* stream);
+/* dx, dresidual (nullable; = dy masked by the ReLU), dgamma, dbeta (C each, overwritten). */
+int mt_bn_act_backward(int N, int C, int HW, int groups, int training, int relu, const float* x, const float* y,
+                       const float* dy, const float* gamma, const float* save_mean, const float* save_invstd,
+                       float* dx, float* dresidual, float* dgamma, float* dbeta, void* stream);
 
 /* Profiling hooks (bench.py roofline, ncu): launch only the stages selected by `stage_mask`
  * of a forward (bit 0 k_proj, 1 k_sim_stats, 2 k_attn, 3 k_out) or backward (bit 0

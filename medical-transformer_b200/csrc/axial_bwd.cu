@@ -10,6 +10,7 @@
 //   k_bwd_proj      bn_qkv backward, dX = W^T dY, dW = dY X^T, and all BN / gate parameter grads
 // P and dZ are recomputed from q,k,v and the saved log-sum-exp; no L x L tensor is stored.
 #include "common.cuh"
+extern thread_local cudaError_t g_last_cuda;
 
 // ============================================================================ shared loaders
 struct BwdSmem {
@@ -350,7 +351,8 @@ static int pow2_le(int x) { int p = 1; while (p * 2 <= x) p *= 2; return p; }
 
 template <typename K>
 static cudaError_t set_smem_b(K kern, size_t bytes) {
-  if (bytes > 48 * 1024) return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  // static shared (reduction scratch, tickets) counts against the 48 KB no-opt-in limit too
+  if (bytes > 32 * 1024) return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   return cudaSuccess;
 }
 
@@ -415,5 +417,6 @@ int axial_backward_launch(const Dims& m, const MtAxialParams& p, const float* x,
   }
   if (mask & 8) nl += launch_bwd_proj(m, p, gr, x, bcoef, yraw, dyh, st);
   *nlaunch = nl;
-  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  g_last_cuda = cudaGetLastError();
+  return g_last_cuda == cudaSuccess ? 0 : -1;
 }

@@ -11,6 +11,7 @@
 // The (B, 3G, L, L) similarity tensor of the reference (100 MB per call at 128 px, 6.4 GB
 // at 512 px) never exists: scores live in registers, one query row per thread.
 #include "common.cuh"
+extern thread_local cudaError_t g_last_cuda;
 
 // ============================================================================ shared loaders
 // qkv BN coefficients (y_hat = a*y_raw + b) of statistic group `grp`, from the table k_proj's last CTA wrote
@@ -229,7 +230,8 @@ static LaunchPlan plan_attn(const Dims& m, int extra_floats_per_strip, int extra
 
 template <typename K>
 static cudaError_t set_smem(K kern, size_t bytes) {
-  if (bytes > 48 * 1024) return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  // static shared (reduction scratch, tickets) counts against the 48 KB no-opt-in limit too
+  if (bytes > 32 * 1024) return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   return cudaSuccess;
 }
 
@@ -278,5 +280,6 @@ int axial_forward_launch(const Dims& m, const MtAxialParams& p, const float* x, 
   }
   if (mask & 8) nl += launch_out(m, coef, oraw, out, st);
   *nlaunch = nl;
-  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  g_last_cuda = cudaGetLastError();
+  return g_last_cuda == cudaSuccess ? 0 : -1;
 }

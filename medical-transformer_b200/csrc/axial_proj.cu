@@ -299,7 +299,9 @@ int launch_bwd_proj(const Dims& m, const MtAxialParams& p, const MtAxialGrads& g
     k_bwd_dx<<<grid, 256, smem, st>>>(m, p, gr, bcoef, yraw, dyh, TS, TL, nTS * nTL, nTL);
   }
   {
-    int ksplit = ntiles < 32 ? ntiles : 32;
+    const int mn = ((2 * m.C + 63) / 64) * ((m.C + 63) / 64);
+    int ksplit = (148 + mn - 1) / mn;                 // fill the 148 SMs: CTAs = Mtiles * Ntiles * ksplit
+    if (ksplit > ntiles) ksplit = ntiles;
     dim3 grid((2 * m.C + 63) / 64, (m.C + 63) / 64, ksplit);
     const size_t smem = sizeof(float) * (2 * 64 * TILE_LD + 6 * (size_t)m.C);
     static bool once = (cudaFuncSetAttribute(k_bwd_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), true);

@@ -16,6 +16,8 @@ struct Dims {
   int dbg;                 // MT_DEBUG_FLAGS env (timing experiments only): bit0 = skip global statistic atomics
   int L, other, B, Bg, gp, d, nt, no, LP, pos;
   float eps, momentum;
+  double inv_n1, inv_n2;   // 1/(Bg*L), 1/(Bg*L*L): element counts of the BN1d / BN2d statistics
+  float unb1, unb2;        // n/(n-1) for the running (unbiased) variance
   // fp64 statistic accumulator layout (per statistic group)
   int f_qkv_sum, f_qkv_sq, f_sim_sum, f_sim_sq, f_out_sum, f_out_sq, nstat_f;
   int b_out_s1, b_out_s2, b_sim_t, b_qkv_s1, b_qkv_s2, nstat_b;
@@ -49,6 +51,8 @@ static inline bool make_dims(const MtAxialDesc* d, Dims& m) {
   m.pos = m.variant != MT_VARIANT_NOPOS;
   m.nt = m.pos ? 3 : 1;
   m.no = m.pos ? 2 : 1;
+  { double n1 = (double)m.Bg * m.L, n2 = n1 * m.L; m.inv_n1 = 1.0 / n1; m.inv_n2 = 1.0 / n2;
+    m.unb1 = n1 > 1 ? (float)(n1 / (n1 - 1.0)) : 1.f; m.unb2 = n2 > 1 ? (float)(n2 / (n2 - 1.0)) : 1.f; }
   m.LP = (m.L % 32 == 0) ? m.L : m.L + 1;      // odd-ish pitch kills bank conflicts when a warp spans heads
   int C = m.C;
   m.f_qkv_sum = 0; m.f_qkv_sq = 2 * C;
@@ -105,47 +109,59 @@ __device__ __forceinline__ size_t nchw_addr(const Dims& m, int b, int c, int l) 
                      : (((size_t)n * m.C + c) * m.H + o) * m.W + l;
 }
 
+// fp64 is used ONLY where cancellation demands it (E[x^2] - E[x]^2, s2 - mu*s1): B200's
+// non-tensor fp64 div / sqrt are ~30-instruction dependent chains on a narrow pipe (measured:
+// a serial tail of 30+ us when the coefficient math was all-double), so everything else is
+// fp32 with a Newton-refined rsqrt.
+__device__ __forceinline__ float rsqrt_nr(float x) {
+  float r = rsqrtf(x);
+  return r * (1.5f - 0.5f * x * r * r);
+}
+struct Moments { float mu, var; double mu_d; };
+__device__ __forceinline__ Moments moments(double sum, double sq, double inv_n) {
+  Moments r;
+  r.mu_d = sum * inv_n;
+  double v = fma(-r.mu_d, r.mu_d, sq * inv_n);
+  r.mu = (float)r.mu_d; r.var = v > 0.0 ? (float)v : 0.f;
+  return r;
+}
+
 // BN as a per-channel affine map of the RAW (un-gated) value x:  y = a*x + b.
-//   training : mean/var from the fp64 accumulators (sum, sumsq over n elements)
+//   training : mean/var from the fp64 accumulators (sum, sumsq; inv_n = 1/count)
 //   eval     : running stats
 // `f` is the gate that multiplies x BEFORE the BN (1 when there is none).
 struct BnCoef { float a, b, mean, var; };
-__device__ __forceinline__ BnCoef bn_coef(int training, double sum, double sq, double n, float f,
+__device__ __forceinline__ BnCoef bn_coef(int training, double sum, double sq, double inv_n, float f,
                                           float gamma, float beta, float rm, float rv, float eps) {
   BnCoef c;
   if (training) {
-    double mu = sum / n;
-    double var = sq / n - mu * mu;
-    if (var < 0.0) var = 0.0;
-    double su2 = (double)f * f * var + (double)eps;      // variance of the gated value + eps
-    double a = (double)gamma * f / sqrt(su2);
-    c.a = (float)a; c.b = (float)((double)beta - a * mu);
-    c.mean = (float)mu; c.var = (float)var;
+    Moments mo = moments(sum, sq, inv_n);
+    const float inv = rsqrt_nr(f * f * mo.var + eps);        // 1/sqrt(variance of the gated value + eps)
+    c.a = gamma * f * inv; c.b = beta - c.a * mo.mu;
+    c.mean = mo.mu; c.var = mo.var;
   } else {
-    double inv = 1.0 / sqrt((double)rv + (double)eps);
-    c.a = (float)((double)gamma * f * inv);
-    c.b = (float)((double)beta - (double)gamma * rm * inv);
+    const float inv = rsqrt_nr(rv + eps);
+    c.a = gamma * f * inv; c.b = beta - gamma * rm * inv;
     c.mean = rm; c.var = rv;
   }
   return c;
 }
 
 // BN backward as an affine map:  dx_raw = A*dy + Bc + Cc*x_raw   (x_raw un-gated).
-//   s1 = sum dy, s2 = sum dy*x_raw over the channel's n elements (training only).
+//   s1 = sum dy, s2 = sum dy*x_raw over the channel's elements (training only).
 struct BnBwdCoef { float A, Bc, Cc; };
-__device__ __forceinline__ BnBwdCoef bn_bwd_coef(int training, double sum, double sq, double n, float f,
+__device__ __forceinline__ BnBwdCoef bn_bwd_coef(int training, double sum, double sq, double inv_n, float f,
                                                  float gamma, float rv, float eps, double s1, double s2) {
   BnBwdCoef r;
   if (training) {
-    double mu = sum / n;
-    double var = sq / n - mu * mu;
-    if (var < 0.0) var = 0.0;
-    double su2 = (double)f * f * var + (double)eps;
-    double a = (double)gamma * f / sqrt(su2);
-    double cc = -a * (double)f * f * (s2 - mu * s1) / (n * su2);
-    r.A = (float)a; r.Cc = (float)cc; r.Bc = (float)(-a * s1 / n - cc * mu);
+    Moments mo = moments(sum, sq, inv_n);
+    const float inv = rsqrt_nr(f * f * mo.var + eps);
+    const float a = gamma * f * inv;
+    const float d = (float)(fma(-mo.mu_d, s1, s2) * inv_n);                   // (s2 - mu*s1)/n
+    const float cc = -a * f * f * d * inv * inv;
+    r.A = a; r.Cc = cc; r.Bc = -a * (float)(s1 * inv_n) - cc * mo.mu;
   } else {
-    r.A = (float)((double)gamma * f / sqrt((double)rv + (double)eps)); r.Bc = 0.f; r.Cc = 0.f;
+    r.A = gamma * f * rsqrt_nr(rv + eps); r.Bc = 0.f; r.Cc = 0.f;
   }
   return r;
 }
@@ -163,16 +179,13 @@ __device__ __forceinline__ double stat_get(const Dims& m, const double* base, in
 
 // sequential EMA of the running statistics over the statistic groups (one BN call each)
 __device__ __forceinline__ void ema_update(const Dims& m, float* rm, float* rv, int ch, const double* stats, int nstat,
-                                           int off_sum, int off_sq, double n, float f) {
+                                           int off_sum, int off_sq, double inv_n, float unbias, float f) {
   float m_ = rm[ch], v_ = rv[ch];
   const float mom = m.momentum;
   for (int g = 0; g < m.ngroups; ++g) {
-    double sum = stat_get(m, stats, g, nstat, off_sum + ch), sq = stat_get(m, stats, g, nstat, off_sq + ch);
-    double mu = sum / n, var = sq / n - mu * mu;
-    if (var < 0.0) var = 0.0;
-    double mu_u = f * mu, var_u = (double)f * f * var * (n / (n - 1.0));
-    m_ = (1.f - mom) * m_ + mom * (float)mu_u;
-    v_ = (1.f - mom) * v_ + mom * (float)var_u;
+    Moments mo = moments(stat_get(m, stats, g, nstat, off_sum + ch), stat_get(m, stats, g, nstat, off_sq + ch), inv_n);
+    m_ = (1.f - mom) * m_ + mom * (f * mo.mu);
+    v_ = (1.f - mom) * v_ + mom * (f * f * mo.var * unbias);
   }
   rm[ch] = m_; rv[ch] = v_;
 }
@@ -195,7 +208,7 @@ __device__ __forceinline__ float gate_val(const float* p) { return p ? __ldg(p) 
 
 // ---- forward coefficient finalisers (all threads of ONE CTA) ---------------------------------
 __device__ __forceinline__ void fin_qkv(const Dims& m, const MtAxialParams& p, const double* stats, float* coef) {
-  const double n = (double)m.Bg * m.L;
+  const double n = m.inv_n1;
   for (int k = threadIdx.x; k < m.ngroups * 2 * m.C; k += blockDim.x) {
     const int g = k / (2 * m.C), ch = k - g * 2 * m.C;
     BnCoef c = bn_coef(m.training, m.training ? stat_get(m, stats, g, m.nstat_f, m.f_qkv_sum + ch) : 0.0,
@@ -206,10 +219,10 @@ __device__ __forceinline__ void fin_qkv(const Dims& m, const MtAxialParams& p, c
   }
   if (m.training)
     for (int ch = threadIdx.x; ch < 2 * m.C; ch += blockDim.x)
-      ema_update(m, p.bn_qkv_rm, p.bn_qkv_rv, ch, stats, m.nstat_f, m.f_qkv_sum, m.f_qkv_sq, n, 1.f);
+      ema_update(m, p.bn_qkv_rm, p.bn_qkv_rv, ch, stats, m.nstat_f, m.f_qkv_sum, m.f_qkv_sq, n, m.unb1, 1.f);
 }
 __device__ __forceinline__ void fin_sim(const Dims& m, const MtAxialParams& p, const double* stats, float* coef) {
-  const double n = (double)m.Bg * m.L * m.L;
+  const double n = m.inv_n2;
   const int nch = m.nt * MT_G;
   for (int k = threadIdx.x; k < m.ngroups * nch; k += blockDim.x) {
     const int g = k / nch, ch = k - g * nch, t = ch / MT_G;
@@ -224,11 +237,11 @@ __device__ __forceinline__ void fin_sim(const Dims& m, const MtAxialParams& p, c
     for (int ch = threadIdx.x; ch < nch; ch += blockDim.x) {
       const int t = ch / MT_G;
       const float f = t == 0 ? 1.f : (t == 1 ? gate_val(p.f_qr) : gate_val(p.f_kr));
-      ema_update(m, p.bn_sim_rm, p.bn_sim_rv, ch, stats, m.nstat_f, m.f_sim_sum, m.f_sim_sq, n, f);
+      ema_update(m, p.bn_sim_rm, p.bn_sim_rv, ch, stats, m.nstat_f, m.f_sim_sum, m.f_sim_sq, n, m.unb2, f);
     }
 }
 __device__ __forceinline__ void fin_out(const Dims& m, const MtAxialParams& p, const double* stats, float* coef) {
-  const double n = (double)m.Bg * m.L;
+  const double n = m.inv_n1;
   const int nch = m.no * m.C;
   for (int k = threadIdx.x; k < m.ngroups * nch; k += blockDim.x) {
     const int g = k / nch, ch = k - g * nch;
@@ -242,14 +255,14 @@ __device__ __forceinline__ void fin_out(const Dims& m, const MtAxialParams& p, c
   if (m.training)
     for (int ch = threadIdx.x; ch < nch; ch += blockDim.x) {
       const float f = (m.no == 2 && (ch & 1)) ? gate_val(p.f_sve) : gate_val(p.f_sv);
-      ema_update(m, p.bn_out_rm, p.bn_out_rv, ch, stats, m.nstat_f, m.f_out_sum, m.f_out_sq, n, f);
+      ema_update(m, p.bn_out_rm, p.bn_out_rv, ch, stats, m.nstat_f, m.f_out_sum, m.f_out_sq, n, m.unb1, f);
     }
 }
 
 // ---- backward coefficient finalisers ------------------------------------------------------------
 __device__ __forceinline__ void fin_bwd_out(const Dims& m, const MtAxialParams& p, const double* stats,
                                             const double* bstats, float* coef) {
-  const double n = (double)m.Bg * m.L;
+  const double n = m.inv_n1;
   const int nch = m.no * m.C;
   for (int k = threadIdx.x; k < m.ngroups * nch; k += blockDim.x) {
     const int g = k / nch, ch = k - g * nch;
@@ -264,7 +277,7 @@ __device__ __forceinline__ void fin_bwd_out(const Dims& m, const MtAxialParams& 
 }
 __device__ __forceinline__ void fin_bwd_sim(const Dims& m, const MtAxialParams& p, const double* stats,
                                             const double* bstats, float* coef) {
-  const double n = (double)m.Bg * m.L * m.L;
+  const double n = m.inv_n2;
   const int nch = m.nt * MT_G;
   for (int k = threadIdx.x; k < m.ngroups * nch; k += blockDim.x) {
     const int g = k / nch, ch = k - g * nch, t = ch / MT_G;
@@ -279,7 +292,7 @@ __device__ __forceinline__ void fin_bwd_sim(const Dims& m, const MtAxialParams& 
 }
 __device__ __forceinline__ void fin_bwd_qkv(const Dims& m, const MtAxialParams& p, const double* stats,
                                             const double* bstats, float* coef) {
-  const double n = (double)m.Bg * m.L;
+  const double n = m.inv_n1;
   for (int k = threadIdx.x; k < m.ngroups * 2 * m.C; k += blockDim.x) {
     const int g = k / (2 * m.C), ch = k - g * 2 * m.C;
     BnBwdCoef c = bn_bwd_coef(m.training, m.training ? stat_get(m, stats, g, m.nstat_f, m.f_qkv_sum + ch) : 0.0,
@@ -293,82 +306,80 @@ __device__ __forceinline__ void fin_bwd_qkv(const Dims& m, const MtAxialParams& 
 
 // ============================================================================ parameter gradients
 __device__ __forceinline__ void bwd_param_grads(const Dims& m, const MtAxialParams& p, const MtAxialGrads& gr,
-                                const double* stats, const double* bstats) {
+                                                const double* stats, const double* bstats) {
+  // d gamma = sum dy*xhat, d beta = sum dy, gate grads in closed form (eps/sigma^3 identity);
+  // only (s2 - mu*s1) is formed in fp64.
   const int tid = threadIdx.x, nthr = blockDim.x, C = m.C, NO = m.no, NOC = NO * C, NT = m.nt;
   for (int ch = tid; ch < 2 * C; ch += nthr) {
-    double dg = 0.0, db = 0.0;
+    float dg = 0.f, db = 0.f;
     for (int g = 0; g < m.ngroups; ++g) {
-      const double n = (double)m.Bg * m.L;
       const double s1 = stat_get(m, bstats, g, m.nstat_b, m.b_qkv_s1 + ch), s2 = stat_get(m, bstats, g, m.nstat_b, m.b_qkv_s2 + ch);
       if (m.training) {
-        double mu = stat_get(m, stats, g, m.nstat_f, m.f_qkv_sum + ch) / n;
-        double var = stat_get(m, stats, g, m.nstat_f, m.f_qkv_sq + ch) / n - mu * mu;
-        if (var < 0.0) var = 0.0;
-        dg += (s2 - mu * s1) / sqrt(var + (double)m.eps);
+        Moments mo = moments(stat_get(m, stats, g, m.nstat_f, m.f_qkv_sum + ch), stat_get(m, stats, g, m.nstat_f, m.f_qkv_sq + ch), m.inv_n1);
+        dg += (float)fma(-mo.mu_d, s1, s2) * rsqrt_nr(mo.var + m.eps);
       } else {
-        dg += (s2 - (double)p.bn_qkv_rm[ch] * s1) / sqrt((double)p.bn_qkv_rv[ch] + (double)m.eps);
+        dg += (float)fma(-(double)p.bn_qkv_rm[ch], s1, s2) * rsqrt_nr(p.bn_qkv_rv[ch] + m.eps);
       }
-      db += s1;
+      db += (float)s1;
     }
-    if (gr.dbn_qkv_w) gr.dbn_qkv_w[ch] = (float)dg;
-    if (gr.dbn_qkv_b) gr.dbn_qkv_b[ch] = (float)db;
+    if (gr.dbn_qkv_w) gr.dbn_qkv_w[ch] = dg;
+    if (gr.dbn_qkv_b) gr.dbn_qkv_b[ch] = db;
   }
-  double gpart[4] = {0.0, 0.0, 0.0, 0.0};
+  float gpart[4] = {0.f, 0.f, 0.f, 0.f};
   for (int ch = tid; ch < NOC; ch += nthr) {
     const int sidx = NO == 2 ? (ch & 1) : 0;
     const float f = sidx ? gate_val(p.f_sve) : gate_val(p.f_sv);
-    const double gam = p.bn_out_w[ch];
-    double dg = 0.0, db = 0.0;
+    const float gam = p.bn_out_w[ch];
+    float dg = 0.f, db = 0.f;
     for (int g = 0; g < m.ngroups; ++g) {
-      const double n = (double)m.Bg * m.L;
       const double s1 = stat_get(m, bstats, g, m.nstat_b, m.b_out_s1 + ch / NO), s2 = stat_get(m, bstats, g, m.nstat_b, m.b_out_s2 + ch);
       if (m.training) {
-        double mu = stat_get(m, stats, g, m.nstat_f, m.f_out_sum + ch) / n;
-        double var = stat_get(m, stats, g, m.nstat_f, m.f_out_sq + ch) / n - mu * mu;
-        if (var < 0.0) var = 0.0;
-        const double su2 = (double)f * f * var + (double)m.eps, su = sqrt(su2);
-        dg += (double)f * (s2 - mu * s1) / su;
-        gpart[2 + sidx] += gam * (s2 - mu * s1) * (double)m.eps / (su2 * su);
+        Moments mo = moments(stat_get(m, stats, g, m.nstat_f, m.f_out_sum + ch), stat_get(m, stats, g, m.nstat_f, m.f_out_sq + ch), m.inv_n1);
+        const float inv = rsqrt_nr(f * f * mo.var + m.eps), d = (float)fma(-mo.mu_d, s1, s2);
+        dg += f * d * inv;
+        gpart[2 + sidx] += gam * d * m.eps * inv * inv * inv;
       } else {
-        const double inv = 1.0 / sqrt((double)p.bn_out_rv[ch] + (double)m.eps);
-        dg += ((double)f * s2 - (double)p.bn_out_rm[ch] * s1) * inv;
-        gpart[2 + sidx] += gam * inv * s2;
+        const float inv = rsqrt_nr(p.bn_out_rv[ch] + m.eps);
+        dg += (f * (float)s2 - p.bn_out_rm[ch] * (float)s1) * inv;
+        gpart[2 + sidx] += gam * inv * (float)s2;
       }
-      db += s1;
+      db += (float)s1;
     }
-    if (gr.dbn_out_w) gr.dbn_out_w[ch] = (float)dg;
-    if (gr.dbn_out_b) gr.dbn_out_b[ch] = (float)db;
+    if (gr.dbn_out_w) gr.dbn_out_w[ch] = dg;
+    if (gr.dbn_out_b) gr.dbn_out_b[ch] = db;
   }
   if (tid < NT * MT_G) {
     const int ch = tid, t = ch / MT_G;
     const float f = t == 0 ? 1.f : (t == 1 ? gate_val(p.f_qr) : gate_val(p.f_kr));
-    const double gam = p.bn_sim_w[ch];
-    double dg = 0.0;
+    const float gam = p.bn_sim_w[ch];
+    float dg = 0.f;
     for (int g = 0; g < m.ngroups; ++g) {
-      const double n = (double)m.Bg * m.L * m.L, T = stat_get(m, bstats, g, m.nstat_b, m.b_sim_t + ch);
+      const float T = (float)stat_get(m, bstats, g, m.nstat_b, m.b_sim_t + ch);
       if (m.training) {
-        double mu = stat_get(m, stats, g, m.nstat_f, m.f_sim_sum + ch) / n;
-        double var = stat_get(m, stats, g, m.nstat_f, m.f_sim_sq + ch) / n - mu * mu;
-        if (var < 0.0) var = 0.0;
-        const double su2 = (double)f * f * var + (double)m.eps, su = sqrt(su2);
-        dg += (double)f * T / su;
-        if (t > 0) gpart[t - 1] += gam * T * (double)m.eps / (su2 * su);
+        Moments mo = moments(stat_get(m, stats, g, m.nstat_f, m.f_sim_sum + ch), stat_get(m, stats, g, m.nstat_f, m.f_sim_sq + ch), m.inv_n2);
+        const float inv = rsqrt_nr(f * f * mo.var + m.eps);
+        dg += f * T * inv;
+        if (t > 0) gpart[t - 1] += gam * T * m.eps * inv * inv * inv;
       } else {
-        const double inv = 1.0 / sqrt((double)p.bn_sim_rv[ch] + (double)m.eps);
-        dg += (double)f * T * inv;
+        const float inv = rsqrt_nr(p.bn_sim_rv[ch] + m.eps);
+        dg += f * T * inv;
         if (t > 0) gpart[t - 1] += gam * inv * T;
       }
     }
-    if (gr.dbn_sim_w) gr.dbn_sim_w[ch] = (float)dg;
+    if (gr.dbn_sim_w) gr.dbn_sim_w[ch] = dg;
     if (gr.dbn_sim_b) gr.dbn_sim_b[ch] = 0.f;        // sum dZ == 0: softmax is shift invariant
   }
-  __shared__ double gred[4][256];                      // fixed-order block reduce -> deterministic
-  for (int k = 0; k < 4; ++k) gred[k][tid] = gpart[k];
+  // block reduce of the four gate partials: warp shuffles, then a fixed-order sum over warps
+  __shared__ float gred[4][32];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float v = seg_sum(gpart[k], 32);
+    if ((tid & 31) == 0) gred[k][tid >> 5] = v;
+  }
   __syncthreads();
   if (tid < 4 && gr.dgates) {
-    double t = 0.0;
-    for (int k = 0; k < nthr && k < 256; ++k) t += gred[tid][k];
-    gr.dgates[tid] = (float)t;
+    float t = 0.f;
+    for (int k = 0; k < (nthr + 31) / 32; ++k) t += gred[tid][k];
+    gr.dgates[tid] = t;
   }
 }
-

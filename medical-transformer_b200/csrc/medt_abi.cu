@@ -11,13 +11,15 @@ int axial_backward_launch(const Dims& m, const MtAxialParams& p, const float* x,
 
 static thread_local char g_err[512] = "";
 static thread_local int g_launches = 0;
+thread_local cudaError_t g_last_cuda = cudaSuccess;   // set by the launchers when a runtime call fails
 
 static int fail(int code, const char* msg) {
   snprintf(g_err, sizeof(g_err), "%s", msg);
   return code;
 }
+int mt_fail_msg(int code, const char* msg) { return fail(code, msg); }
 static int fail_cuda(const char* where) {
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = g_last_cuda != cudaSuccess ? g_last_cuda : cudaGetLastError();
   snprintf(g_err, sizeof(g_err), "%s: CUDA error %d (%s)", where, (int)e, cudaGetErrorString(e));
   return MT_ERR_CUDA;
 }

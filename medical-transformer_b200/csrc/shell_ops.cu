@@ -1,0 +1,265 @@
+// shell_ops.cu -- the glue of the conv shell around the axial ops, as fused sm_100a kernels:
+//
+//   mt_up2x_relu_add_*  relu(F.interpolate(x, scale 2, bilinear, align_corners=False)) + skip
+//                       (one decoder step, reference axialnet.py:493-501, 650-652, 690-698)
+//   mt_bn_act_*         BatchNorm2d with batch statistics (+ residual) (+ ReLU), per statistic
+//                       group: AxialBlock*.forward :285-300 / :327-342 / :373-389, the stems
+//                       :475-483, and the 16 per-patch BN calls of the LoGo loop :661-700 batched
+//                       as 16 groups with the reference's sequential running-stat updates.
+// All fp32, NCHW.  HBM-bound elementwise / reduction work: coalesced float loads along W,
+// one CTA per (group, channel) for the reductions.
+#include <stdio.h>
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// bilinear x2, align_corners=False:  src = dst/2 - 0.25 clamped at 0
+__device__ __forceinline__ void up_taps(int dst, int n_in, int& i0, int& i1, float& lam) {
+  float src = 0.5f * (float)dst - 0.25f;
+  if (src < 0.f) src = 0.f;
+  i0 = (int)src;
+  lam = src - (float)i0;
+  i1 = i0 + 1 < n_in ? i0 + 1 : n_in - 1;
+}
+
+// one thread per output pixel pair along W (float2 store); mask byte = (pre-activation > 0)
+__global__ void __launch_bounds__(256)
+k_up2x_fwd(int planes, int H, int W, const float* __restrict__ in, const float* __restrict__ skip,
+           float* __restrict__ out, unsigned char* __restrict__ mask) {
+  const int Wo = 2 * W, Ho = 2 * H;
+  const long total = (long)planes * Ho * W;                 // W pairs per output row
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int wp = (int)(idx % W);
+  const long t = idx / W;
+  const int ho = (int)(t % Ho);
+  const long pl = t / Ho;
+  int h0, h1; float lh;
+  up_taps(ho, H, h0, h1, lh);
+  const float* r0 = in + (pl * H + h0) * W;
+  const float* r1 = in + (pl * H + h1) * W;
+  const int wm = wp > 0 ? wp - 1 : 0, wpl = wp + 1 < W ? wp + 1 : W - 1;
+  // columns: out 2wp uses (wp-1, wp) with lam 0.75 (or clamp), out 2wp+1 uses (wp, wp+1) with lam 0.25
+  const float a_m = (1.f - lh) * __ldg(r0 + wm) + lh * __ldg(r1 + wm);
+  const float a_c = (1.f - lh) * __ldg(r0 + wp) + lh * __ldg(r1 + wp);
+  const float a_p = (1.f - lh) * __ldg(r0 + wpl) + lh * __ldg(r1 + wpl);
+  float v0 = wp > 0 ? 0.25f * a_m + 0.75f * a_c : a_c;
+  float v1 = 0.75f * a_c + 0.25f * a_p;                     // at wp == W-1: a_p == a_c -> a_c
+  const long o = (pl * Ho + ho) * Wo + 2 * wp;
+  unsigned char m0 = v0 > 0.f, m1 = v1 > 0.f;
+  v0 = m0 ? v0 : 0.f; v1 = m1 ? v1 : 0.f;
+  if (skip) { const float2 s = __ldg(reinterpret_cast<const float2*>(skip + o)); v0 += s.x; v1 += s.y; }
+  *reinterpret_cast<float2*>(out + o) = make_float2(v0, v1);
+  if (mask) { mask[o] = m0; mask[o + 1] = m1; }
+}
+
+// gather form: one thread per input pixel sums its (up to) 4x4 masked output gradients
+__global__ void __launch_bounds__(256)
+k_up2x_bwd(int planes, int H, int W, const float* __restrict__ dout, const unsigned char* __restrict__ mask,
+           float* __restrict__ din) {
+  const long total = (long)planes * H * W;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int w = (int)(idx % W);
+  const long t = idx / W;
+  const int h = (int)(t % H);
+  const long pl = t / H;
+  const int Wo = 2 * W, Ho = 2 * H;
+  float wr[4], wc[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = 2 * h - 1 + k, cidx = 2 * w - 1 + k;
+    int i0, i1; float lam;
+    wr[k] = 0.f; wc[k] = 0.f;
+    if (r >= 0 && r < Ho) { up_taps(r, H, i0, i1, lam); wr[k] = (i0 == h ? 1.f - lam : 0.f) + (i1 == h ? lam : 0.f); }
+    if (cidx >= 0 && cidx < Wo) { up_taps(cidx, W, i0, i1, lam); wc[k] = (i0 == w ? 1.f - lam : 0.f) + (i1 == w ? lam : 0.f); }
+  }
+  float acc = 0.f;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    if (wr[a] == 0.f) continue;
+    const int r = 2 * h - 1 + a;
+    const long base = (pl * Ho + r) * Wo;
+    float rowacc = 0.f;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      if (wc[b] == 0.f) continue;
+      const long o = base + 2 * w - 1 + b;
+      const float g = mask[o] ? __ldg(dout + o) : 0.f;
+      rowacc = fmaf(wc[b], g, rowacc);
+    }
+    acc = fmaf(wr[a], rowacc, acc);
+  }
+  din[idx] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// BatchNorm2d (+residual)(+ReLU), one CTA per (channel, statistic group)
+struct BnActArgs {
+  int N, C, HW, G, training, relu;
+  float eps, momentum;
+};
+
+__device__ __forceinline__ float2 block_sum2(float a, float b) {
+  __shared__ float ra[32], rb[32];
+  a = seg_sum(a, 32); b = seg_sum(b, 32);
+  const int wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { ra[wid] = a; rb[wid] = b; }
+  __syncthreads();
+  float sa = 0.f, sb = 0.f;
+  for (int k = 0; k < nw; ++k) { sa += ra[k]; sb += rb[k]; }      // fixed order: deterministic
+  return make_float2(sa, sb);
+}
+
+__global__ void __launch_bounds__(256)
+k_bn_act_fwd(BnActArgs a, const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ gamma,
+             const float* __restrict__ beta, float* __restrict__ rm, float* __restrict__ rv, float* __restrict__ y,
+             float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  const int c = blockIdx.x, g = blockIdx.y;
+  const int npg = a.N / a.G, cnt = npg * a.HW;
+  float mean, invstd;
+  if (a.training) {
+    // pass 1: shifted sums (shift = first element) keep the fp32 variance well conditioned
+    const float shift = __ldg(x + ((size_t)(g * npg) * a.C + c) * a.HW);
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const int n = i / a.HW, r = i - n * a.HW;
+      const float v = __ldg(x + ((size_t)(g * npg + n) * a.C + c) * a.HW + r) - shift;
+      s1 += v; s2 = fmaf(v, v, s2);
+    }
+    const float2 s = block_sum2(s1, s2);
+    const float inv_n = 1.f / (float)cnt;
+    const float ms = s.x * inv_n;
+    float var = s.y * inv_n - ms * ms;
+    var = var > 0.f ? var : 0.f;
+    mean = ms + shift;
+    invstd = rsqrt_nr(var + a.eps);
+    if (threadIdx.x == 0) {
+      save_mean[g * a.C + c] = mean; save_invstd[g * a.C + c] = invstd;
+      save_mean[(a.G + g) * a.C + c] = var;                 // biased variance, for the EMA below
+    }
+  } else {
+    mean = rm[c]; invstd = rsqrt_nr(rv[c] + a.eps);
+    if (threadIdx.x == 0) { save_mean[g * a.C + c] = mean; save_invstd[g * a.C + c] = invstd; }
+  }
+  const float ga = gamma[c] * invstd, be = beta[c] - mean * ga;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const int n = i / a.HW, r = i - n * a.HW;
+    const size_t o = ((size_t)(g * npg + n) * a.C + c) * a.HW + r;
+    float v = fmaf(ga, __ldg(x + o), be);
+    if (res) v += __ldg(res + o);
+    if (a.relu) v = v > 0.f ? v : 0.f;
+    y[o] = v;
+  }
+}
+
+// sequential running-stat EMA over the statistic groups (one BN call per group in the reference)
+__global__ void k_bn_ema(BnActArgs a, const float* __restrict__ save_mean, float* __restrict__ rm, float* __restrict__ rv) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.C) return;
+  const float cnt = (float)(a.N / a.G) * a.HW;
+  const float unb = cnt > 1.f ? cnt / (cnt - 1.f) : 1.f;
+  float m_ = rm[c], v_ = rv[c];
+  for (int g = 0; g < a.G; ++g) {
+    m_ = (1.f - a.momentum) * m_ + a.momentum * save_mean[g * a.C + c];
+    v_ = (1.f - a.momentum) * v_ + a.momentum * save_mean[(a.G + g) * a.C + c] * unb;
+  }
+  rm[c] = m_; rv[c] = v_;
+}
+
+// dx (and d residual = masked dy), dgamma / dbeta accumulated over groups
+__global__ void __launch_bounds__(256)
+k_bn_act_bwd(BnActArgs a, const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dy,
+             const float* __restrict__ gamma, const float* __restrict__ save_mean, const float* __restrict__ save_invstd,
+             float* __restrict__ dx, float* __restrict__ dres, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x, g = blockIdx.y;
+  const int npg = a.N / a.G, cnt = npg * a.HW;
+  const float mean = save_mean[g * a.C + c], invstd = save_invstd[g * a.C + c];
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const int n = i / a.HW, r = i - n * a.HW;
+    const size_t o = ((size_t)(g * npg + n) * a.C + c) * a.HW + r;
+    float d = __ldg(dy + o);
+    if (a.relu && !(__ldg(y + o) > 0.f)) d = 0.f;
+    s1 += d; s2 = fmaf(d, (__ldg(x + o) - mean) * invstd, s2);
+  }
+  const float2 s = block_sum2(s1, s2);
+  if (threadIdx.x == 0) {
+    if (a.G == 1) { dgamma[c] = s.y; dbeta[c] = s.x; }
+    else { atomicAdd(dgamma + c, s.y); atomicAdd(dbeta + c, s.x); }
+  }
+  const float ga = gamma[c] * invstd, inv_n = 1.f / (float)cnt;
+  const float m1 = a.training ? s.x * inv_n : 0.f, m2 = a.training ? s.y * inv_n : 0.f;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const int n = i / a.HW, r = i - n * a.HW;
+    const size_t o = ((size_t)(g * npg + n) * a.C + c) * a.HW + r;
+    float d = __ldg(dy + o);
+    if (a.relu && !(__ldg(y + o) > 0.f)) d = 0.f;
+    if (dres) dres[o] = d;
+    const float xh = (__ldg(x + o) - mean) * invstd;
+    dx[o] = ga * (d - m1 - xh * m2);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+extern thread_local cudaError_t g_last_cuda;
+int mt_fail_msg(int code, const char* msg);
+
+extern "C" {
+
+int mt_up2x_relu_add_forward(int planes, int H, int W, const float* in, const float* skip, float* out,
+                             unsigned char* mask, void* stream) {
+  if (planes <= 0 || H <= 0 || W <= 0 || !in || !out) return mt_fail_msg(MT_ERR_BAD_ARG, "mt_up2x_relu_add_forward: bad argument");
+  const long total = (long)planes * 2 * H * W;
+  k_up2x_fwd<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(planes, H, W, in, skip, out, mask);
+  g_last_cuda = cudaGetLastError();
+  return g_last_cuda == cudaSuccess ? MT_OK : mt_fail_msg(MT_ERR_CUDA, "mt_up2x_relu_add_forward: launch failed");
+}
+
+int mt_up2x_relu_add_backward(int planes, int H, int W, const float* dout, const unsigned char* mask, float* din,
+                              void* stream) {
+  if (planes <= 0 || H <= 0 || W <= 0 || !dout || !mask || !din) return mt_fail_msg(MT_ERR_BAD_ARG, "mt_up2x_relu_add_backward: bad argument");
+  const long total = (long)planes * H * W;
+  k_up2x_bwd<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(planes, H, W, dout, mask, din);
+  g_last_cuda = cudaGetLastError();
+  return g_last_cuda == cudaSuccess ? MT_OK : mt_fail_msg(MT_ERR_CUDA, "mt_up2x_relu_add_backward: launch failed");
+}
+
+int mt_bn_act_forward(int N, int C, int HW, int groups, int training, int relu, float eps, float momentum,
+                      const float* x, const float* residual, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, float* y, float* save_mean, float* save_invstd,
+                      void* stream) {
+  if (N <= 0 || C <= 0 || HW <= 0 || groups <= 0 || N % groups || !x || !gamma || !beta || !running_mean || !running_var ||
+      !y || !save_mean || !save_invstd)
+    return mt_fail_msg(MT_ERR_BAD_ARG, "mt_bn_act_forward: bad argument");
+  if (training && (long)(N / groups) * HW < 2) return mt_fail_msg(MT_ERR_BAD_ARG, "mt_bn_act_forward: training needs more than one value per channel");
+  BnActArgs a{N, C, HW, groups, training, relu, eps, momentum};
+  const int cnt = (N / groups) * HW;
+  const int bs = cnt >= 256 ? 256 : (cnt >= 128 ? 128 : 64);
+  k_bn_act_fwd<<<dim3(C, groups), bs, 0, (cudaStream_t)stream>>>(a, x, residual, gamma, beta, running_mean, running_var, y,
+                                                                   save_mean, save_invstd);
+  if (training) k_bn_ema<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a, save_mean, running_mean, running_var);
+  g_last_cuda = cudaGetLastError();
+  return g_last_cuda == cudaSuccess ? MT_OK : mt_fail_msg(MT_ERR_CUDA, "mt_bn_act_forward: launch failed");
+}
+
+int mt_bn_act_backward(int N, int C, int HW, int groups, int training, int relu, const float* x, const float* y,
+                       const float* dy, const float* gamma, const float* save_mean, const float* save_invstd,
+                       float* dx, float* dresidual, float* dgamma, float* dbeta, void* stream) {
+  if (N <= 0 || C <= 0 || HW <= 0 || groups <= 0 || N % groups || !x || !y || !dy || !gamma || !save_mean || !save_invstd ||
+      !dx || !dgamma || !dbeta)
+    return mt_fail_msg(MT_ERR_BAD_ARG, "mt_bn_act_backward: bad argument");
+  BnActArgs a{N, C, HW, groups, training, relu, 0.f, 0.f};
+  if (groups > 1) {
+    cudaMemsetAsync(dgamma, 0, sizeof(float) * C, (cudaStream_t)stream);
+    cudaMemsetAsync(dbeta, 0, sizeof(float) * C, (cudaStream_t)stream);
+  }
+  const int cnt = (N / groups) * HW;
+  const int bs = cnt >= 256 ? 256 : (cnt >= 128 ? 128 : 64);
+  k_bn_act_bwd<<<dim3(C, groups), bs, 0, (cudaStream_t)stream>>>(a, x, y, dy, gamma, save_mean, save_invstd, dx, dresidual,
+                                                                   dgamma, dbeta);
+  g_last_cuda = cudaGetLastError();
+  return g_last_cuda == cudaSuccess ? MT_OK : mt_fail_msg(MT_ERR_CUDA, "mt_bn_act_backward: launch failed");
+}
+
+}  // extern "C"

@@ -20,7 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from medt_b200.axial_op import axial_attention
-from medt_b200.grouped_bn import batch_norm_grouped
+from medt_b200.shell_ops import bn_act, up2x_relu_add
 
 from .utils import qkv_transform
 
@@ -116,12 +116,11 @@ class _AxialBlockBase(nn.Module):
 
     def forward(self, x):
         g = self._stat_groups
-        out = F.relu(batch_norm_grouped(self.conv_down(x), self.bn1, g))
+        out = bn_act(self.conv_down(x), self.bn1, g, relu=True)
         out = self.width_block(self.hight_block(out))
-        out = batch_norm_grouped(self.conv_up(F.relu(out)), self.bn2, g)
         if self.downsample is not None:
-            x = batch_norm_grouped(self.downsample[0](x), self.downsample[1], g)
-        return F.relu(out + x)
+            x = bn_act(self.downsample[0](x), self.downsample[1], g, relu=False)
+        return bn_act(self.conv_up(F.relu(out)), self.bn2, g, relu=True, residual=x)
 
 
 class AxialBlock(_AxialBlockBase):
@@ -138,9 +137,9 @@ class AxialBlock_wopos(_AxialBlockBase):
 
 
 # ----------------------------------------------------------------------------- shells
-def _up_relu(conv, x):
-    """relu(bilinear x2 (conv(x))) -- one decoder step (reference :493-501)."""
-    return F.relu(F.interpolate(conv(x), scale_factor=(2, 2), mode='bilinear'))
+def _up_relu(conv, x, skip=None):
+    """relu(bilinear x2 (conv(x))) [+ skip] -- one decoder step (reference :493-501), one fused kernel."""
+    return up2x_relu_add(conv(x), skip)
 
 
 class _ShellBase(nn.Module):
@@ -174,7 +173,7 @@ class _ShellBase(nn.Module):
     @staticmethod
     def _stem(x, convs, bns, groups=1):
         for conv, bn in zip(convs, bns):
-            x = F.relu(batch_norm_grouped(conv(x), bn, groups))
+            x = bn_act(conv(x), bn, groups, relu=True)
         return x
 
 
@@ -212,10 +211,10 @@ class ResAxialAttentionUNet(_ShellBase):
         x2 = self.layer2(x1)
         x3 = self.layer3(x2)
         x4 = self.layer4(x3)
-        x = _up_relu(self.decoder1, x4) + x4
-        x = _up_relu(self.decoder2, x) + x3
-        x = _up_relu(self.decoder3, x) + x2
-        x = _up_relu(self.decoder4, x) + x1
+        x = _up_relu(self.decoder1, x4, x4)
+        x = _up_relu(self.decoder2, x, x3)
+        x = _up_relu(self.decoder3, x, x2)
+        x = _up_relu(self.decoder4, x, x1)
         x = _up_relu(self.decoder5, x)
         return self.adjust(F.relu(x))
 
@@ -286,10 +285,10 @@ class medt_net(_ShellBase):
         x2 = self.layer2_p(x1)
         x3 = self.layer3_p(x2)
         x4 = self.layer4_p(x3)
-        xp = _up_relu(self.decoder1_p, x4) + x4
-        xp = _up_relu(self.decoder2_p, xp) + x3
-        xp = _up_relu(self.decoder3_p, xp) + x2
-        xp = _up_relu(self.decoder4_p, xp) + x1
+        xp = _up_relu(self.decoder1_p, x4, x4)
+        xp = _up_relu(self.decoder2_p, xp, x3)
+        xp = _up_relu(self.decoder3_p, xp, x2)
+        xp = _up_relu(self.decoder4_p, xp, x1)
         xp = _up_relu(self.decoder5_p, xp)
         c = xp.shape[1]
         return xp.reshape(GRID, GRID, n, c, PATCH, PATCH).permute(2, 3, 0, 4, 1, 5).reshape(n, c, side, side)
@@ -299,7 +298,7 @@ class medt_net(_ShellBase):
         x = self._stem(x, (self.conv1, self.conv2, self.conv3), (self.bn1, self.bn2, self.bn3))
         x1 = self.layer1(x)
         x2 = self.layer2(x1)
-        x = _up_relu(self.decoder4, x2) + x1
+        x = _up_relu(self.decoder4, x2, x1)
         x = _up_relu(self.decoder5, x)
         side = PATCH * GRID
         x_loc = x.clone()                       # outside the 128x128 patch grid x_loc stays == x (:658,:700)

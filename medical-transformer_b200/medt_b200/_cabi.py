@@ -40,7 +40,8 @@ class MtAxialGrads(C.Structure):
 
 EXPORTS = ["mt_version", "mt_last_error", "mt_last_launch_count", "mt_axial_saved_bytes",
            "mt_axial_bwd_workspace_bytes", "mt_axial_forward", "mt_axial_backward",
-           "mt_axial_forward_stages", "mt_axial_backward_stages"]
+           "mt_axial_forward_stages", "mt_axial_backward_stages",
+           "mt_up2x_relu_add_forward", "mt_up2x_relu_add_backward", "mt_bn_act_forward", "mt_bn_act_backward"]
 
 
 def lib_path() -> str:
@@ -77,6 +78,15 @@ def load_library():
         lib.mt_axial_forward_stages.argtypes = lib.mt_axial_forward.argtypes + [C.c_int]
         lib.mt_axial_backward_stages.restype = C.c_int
         lib.mt_axial_backward_stages.argtypes = lib.mt_axial_backward.argtypes + [C.c_int]
+        VP, I, F_ = C.c_void_p, C.c_int, C.c_float
+        lib.mt_up2x_relu_add_forward.restype = C.c_int
+        lib.mt_up2x_relu_add_forward.argtypes = [I, I, I, VP, VP, VP, VP, VP]
+        lib.mt_up2x_relu_add_backward.restype = C.c_int
+        lib.mt_up2x_relu_add_backward.argtypes = [I, I, I, VP, VP, VP, VP]
+        lib.mt_bn_act_forward.restype = C.c_int
+        lib.mt_bn_act_forward.argtypes = [I, I, I, I, I, I, F_, F_, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP]
+        lib.mt_bn_act_backward.restype = C.c_int
+        lib.mt_bn_act_backward.argtypes = [I, I, I, I, I, I, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP]
         _LIB = lib
         return lib
 

@@ -1,0 +1,126 @@
+"""autograd wrappers of the fused shell kernels (mt_up2x_relu_add_*, mt_bn_act_*).
+
+`up2x_relu_add(x, skip)`  == F.relu(F.interpolate(x, scale_factor=(2,2), mode='bilinear')) + skip
+`bn_act(x, bn, groups, relu, residual)` == [relu](bn(x) [+ residual]) with per-group batch
+statistics (groups > 1 only inside the batched LoGo local branch)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _cabi
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _need_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f"medt_b200.{what}: input is on {t.device}; the B200 path has no CPU fallback")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"medt_b200.{what}: float32 expected, got {t.dtype}")
+
+
+class Up2xReluAdd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, skip):
+        _need_cuda(x, "up2x_relu_add")
+        lib = _cabi.load_library()
+        x = x.contiguous()
+        n, c, h, w = x.shape
+        skip_c = None if skip is None else skip.contiguous()
+        out = torch.empty((n, c, 2 * h, 2 * w), dtype=torch.float32, device=x.device)
+        need_bwd = x.requires_grad or (skip is not None and skip.requires_grad)
+        mask = torch.empty((n, c, 2 * h, 2 * w), dtype=torch.uint8, device=x.device) if need_bwd else None
+        with torch.cuda.device(x.device):
+            rc = lib.mt_up2x_relu_add_forward(n * c, h, w, _p(x), _p(skip_c), _p(out), _p(mask), _stream(x.device))
+        _cabi.check(rc, "mt_up2x_relu_add_forward")
+        _cabi.LAUNCHES["kernels"] += 1
+        ctx.save_for_backward(mask)
+        ctx.shape = (n, c, h, w)
+        ctx.has_skip = skip is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (mask,) = ctx.saved_tensors
+        n, c, h, w = ctx.shape
+        lib = _cabi.load_library()
+        dout = dout.contiguous()
+        din = None
+        if ctx.needs_input_grad[0]:
+            din = torch.empty((n, c, h, w), dtype=torch.float32, device=dout.device)
+            with torch.cuda.device(dout.device):
+                rc = lib.mt_up2x_relu_add_backward(n * c, h, w, _p(dout), _p(mask), _p(din), _stream(dout.device))
+            _cabi.check(rc, "mt_up2x_relu_add_backward")
+            _cabi.LAUNCHES["kernels"] += 1
+        return din, (dout if (ctx.has_skip and ctx.needs_input_grad[1]) else None)
+
+
+def up2x_relu_add(x, skip=None):
+    return Up2xReluAdd.apply(x, skip)
+
+
+class BnAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, residual, weight, bias, rm, rv, cfg):
+        groups, training, relu, eps, momentum = cfg
+        _need_cuda(x, "bn_act")
+        lib = _cabi.load_library()
+        x = x.contiguous()
+        res = None if residual is None else residual.contiguous()
+        n, c, h, w = x.shape
+        y = torch.empty_like(x)
+        save_mean = torch.empty((2 * groups, c), dtype=torch.float32, device=x.device)
+        save_invstd = torch.empty((groups, c), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.mt_bn_act_forward(n, c, h * w, groups, int(training), int(relu), eps, momentum, _p(x), _p(res),
+                                       _p(weight), _p(bias), _p(rm), _p(rv), _p(y), _p(save_mean), _p(save_invstd),
+                                       _stream(x.device))
+        _cabi.check(rc, "mt_bn_act_forward")
+        _cabi.LAUNCHES["kernels"] += 2 if training else 1
+        ctx.cfg = cfg
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(x, y, weight, save_mean, save_invstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, weight, save_mean, save_invstd = ctx.saved_tensors
+        groups, training, relu, eps, momentum = ctx.cfg
+        lib = _cabi.load_library()
+        dy = dy.contiguous()
+        n, c, h, w = x.shape
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if (ctx.has_res and ctx.needs_input_grad[1]) else None
+        dg = torch.empty(c, dtype=torch.float32, device=x.device)
+        db = torch.empty(c, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.mt_bn_act_backward(n, c, h * w, groups, int(training), int(relu), _p(x), _p(y), _p(dy), _p(weight),
+                                        _p(save_mean), _p(save_invstd), _p(dx), _p(dres), _p(dg), _p(db), _stream(x.device))
+        _cabi.check(rc, "mt_bn_act_backward")
+        _cabi.LAUNCHES["kernels"] += 1
+        need = ctx.needs_input_grad
+        return (dx if need[0] else None, dres, dg if need[2] else None, db if need[3] else None, None, None, None)
+
+
+def bn_act(x, bn, groups: int = 1, relu: bool = True, residual=None):
+    """[relu](bn(x) [+ residual]); `bn` is the module's own nn.BatchNorm2d (parameters, running
+    statistics and num_batches_tracked are updated exactly as `groups` successive calls would)."""
+    training = bn.training
+    g = groups if training else 1
+    cfg = (int(g), bool(training), bool(relu), float(bn.eps), float(bn.momentum if bn.momentum is not None else 0.1))
+    y = BnAct.apply(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, cfg)
+    if training:
+        if getattr(bn, "_nbt_deferred", False):
+            bn._stat_groups_bn = g
+        else:
+            with torch.no_grad():
+                bn.num_batches_tracked += g
+    return y

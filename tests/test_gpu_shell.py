@@ -1,0 +1,63 @@
+"""GPU tier: the fused shell kernels against plain PyTorch fp32 ops (the reference's own
+F.interpolate / BatchNorm2d / relu / add sequence, axialnet.py:285-300, :493-501, :661-700)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("shape", [(2, 5, 4, 4), (4, 16, 64, 64), (3, 7, 1, 3), (2, 32, 8, 16)])
+@pytest.mark.parametrize("with_skip", [True, False])
+def test_up2x_relu_add_matches_torch(shape, with_skip):
+    from medt_b200.shell_ops import up2x_relu_add
+    torch.manual_seed(1)
+    n, c, h, w = shape
+    x = torch.randn(shape, device="cuda", requires_grad=True)
+    skip = torch.randn(n, c, 2 * h, 2 * w, device="cuda", requires_grad=True) if with_skip else None
+    ref = F.relu(F.interpolate(x, scale_factor=(2, 2), mode="bilinear"))
+    if with_skip:
+        ref = ref + skip
+    got = up2x_relu_add(x, skip)
+    assert torch.allclose(got, ref, atol=1e-6, rtol=1e-6)
+    d = torch.randn_like(ref)
+    gref = torch.autograd.grad(ref, [x] + ([skip] if with_skip else []), d)
+    ggot = torch.autograd.grad(got, [x] + ([skip] if with_skip else []), d)
+    for a, b in zip(ggot, gref):
+        assert torch.allclose(a, b, atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("n,c,h,w,groups", [(4, 8, 64, 64, 1), (4, 128, 64, 64, 1), (32, 16, 4, 4, 16), (6, 5, 3, 7, 3)])
+@pytest.mark.parametrize("relu,with_res,training", [(True, False, True), (True, True, True), (False, False, True), (True, True, False)])
+def test_bn_act_matches_torch(n, c, h, w, groups, relu, with_res, training):
+    from medt_b200.shell_ops import bn_act
+    torch.manual_seed(2)
+    x = (torch.randn(n, c, h, w, device="cuda") * 1.7 + 0.6).requires_grad_(True)
+    res = torch.randn(n, c, h, w, device="cuda", requires_grad=True) if with_res else None
+    a, b = torch.nn.BatchNorm2d(c).cuda(), torch.nn.BatchNorm2d(c).cuda()
+    with torch.no_grad():
+        for bn in (a, b):
+            bn.weight.copy_(torch.linspace(0.5, 1.5, c)); bn.bias.copy_(torch.linspace(-0.3, 0.3, c))
+            bn.running_mean.copy_(torch.linspace(-0.2, 0.4, c)); bn.running_var.copy_(torch.linspace(0.6, 1.4, c))
+    a.train(training); b.train(training)
+    g = groups if training else 1
+    ref = torch.cat([a(xb) for xb in x.chunk(g)], 0)       # the reference's way: one BN call per patch
+    if with_res:
+        ref = ref + res
+    if relu:
+        ref = F.relu(ref)
+    got = bn_act(x, b, groups, relu=relu, residual=res)
+    assert torch.allclose(got, ref, atol=2e-5, rtol=2e-5)
+    assert torch.allclose(a.running_mean, b.running_mean, atol=1e-6) and torch.allclose(a.running_var, b.running_var, atol=1e-5)
+    assert int(a.num_batches_tracked) == int(b.num_batches_tracked)
+    d = torch.randn_like(ref)
+    ins_ref = [x, a.weight, a.bias] + ([res] if with_res else [])
+    ins_got = [x, b.weight, b.bias] + ([res] if with_res else [])
+    for u, v in zip(torch.autograd.grad(got, ins_got, d), torch.autograd.grad(ref, ins_ref, d)):
+        assert (u - v).norm() <= 2e-4 * max(v.norm().item(), 1e-3), (u - v).norm() / v.norm()
+
+
+def test_shell_ops_refuse_cpu():
+    from medt_b200.shell_ops import up2x_relu_add
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        up2x_relu_add(torch.randn(1, 1, 2, 2))
