@@ -1,0 +1,66 @@
+// axial_attn2.cuh -- register-tiled building blocks of the attention passes ("v2").
+//
+// A thread owns RT consecutive rows (or columns) and walks the other index in blocks of RT, so
+//   * q/k/v/dO values of the walked index are one 32*RT-bit shared-memory load per RT pairs;
+//   * the Toeplitz tables relative[c, i-j+L-1] are read through SLIDING REGISTER WINDOWS: the
+//     RT x RT pair block touches only 2*RT-1 distinct diagonals, of which RT are new per step
+//     (one aligned vector load), instead of one scalar load per pair and per table row.
+// ncu on the v1 kernels (profiles/r1_stage_kernels_v1.md): 45 issued warp instructions per 32
+// scores, issue-bound at 21 % warps active; this layout needs ~13-20.
+#pragma once
+#include "common.cuh"
+
+template <int RT> struct VecT;
+template <> struct VecT<4> { typedef float4 T; };
+template <> struct VecT<2> { typedef float2 T; };
+
+template <int RT>
+__device__ __forceinline__ void ldv(float (&d)[RT], const float* p) {
+  typedef typename VecT<RT>::T V;
+  const V v = *reinterpret_cast<const V*>(p);
+  const float* f = reinterpret_cast<const float*>(&v);
+#pragma unroll
+  for (int k = 0; k < RT; ++k) d[k] = f[k];
+}
+
+// window over a table indexed by  own - walk + L - 1  (own = RT*t + r, walk = RT*wb + w):
+//   value(r, w) = T[RT*K - 1 + (r - w)],  K = t + L/RT - wb;  walking forward decrements K.
+template <int RT>
+struct WinA {
+  float hi[RT], lo[RT];
+  __device__ __forceinline__ void init(const float* row, int K) { ldv<RT>(hi, row + RT * K); ldv<RT>(lo, row + RT * (K - 1)); }
+  __device__ __forceinline__ void advance(const float* row, int Knew) {
+#pragma unroll
+    for (int k = 0; k < RT; ++k) hi[k] = lo[k];
+    ldv<RT>(lo, row + RT * (Knew - 1));
+  }
+  __device__ __forceinline__ float get(int r, int w) const { const int d = r - w; return d >= 1 ? hi[d - 1] : lo[RT - 1 + d]; }
+};
+
+// window over a table indexed by  walk - own + L - 1, stored SHIFTED by one (Ts[x] = T[x-1]):
+//   value(r, w) = Ts[RT*K + (w - r)],  K = wb - t + L/RT;  walking forward increments K.
+template <int RT>
+struct WinB {
+  float lo[RT], hi[RT];
+  __device__ __forceinline__ void init(const float* row, int K) { ldv<RT>(hi, row + RT * K); ldv<RT>(lo, row + RT * (K - 1)); }
+  __device__ __forceinline__ void advance(const float* row, int Knew) {
+#pragma unroll
+    for (int k = 0; k < RT; ++k) lo[k] = hi[k];
+    ldv<RT>(hi, row + RT * Knew);
+  }
+  __device__ __forceinline__ float get(int r, int w) const { const int d = w - r; return d >= 0 ? hi[d] : lo[RT + d]; }
+};
+
+// shared-memory pitch of one Toeplitz table row in the v2 layout (plain copy; the shifted copy
+// follows at +RP): 2L entries used, padded so the last window pre-load stays in bounds
+__host__ __device__ __forceinline__ int rel_pitch(int L) { return 2 * L + 8; }
+
+// stage `relative` (2gp rows x (2L-1)) into smem twice: plain T[m] and shifted Ts[m+1]
+__device__ __forceinline__ void load_rel2(const Dims& m, const float* __restrict__ rel, float* Rp, float* Rs) {
+  const int RP = rel_pitch(m.L), RL = 2 * m.L - 1, rows = 2 * m.gp;
+  for (int idx = threadIdx.x; idx < rows * RP; idx += blockDim.x) {
+    const int c = idx / RP, x = idx - c * RP;
+    Rp[idx] = x < RL ? __ldg(rel + c * RL + x) : 0.f;
+    Rs[idx] = (x >= 1 && x <= RL) ? __ldg(rel + c * RL + x - 1) : 0.f;
+  }
+}

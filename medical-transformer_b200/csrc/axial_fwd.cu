@@ -210,6 +210,10 @@ int launch_proj(const Dims& m, const MtAxialParams& p, const float* x, float* yr
                 unsigned* cnt, cudaStream_t st);
 int launch_out(const Dims& m, const float* coef, const float* oraw, float* out, cudaStream_t st);
 
+template <int MODE>
+int launch_attn2(const Dims& m, const MtAxialParams& p, const float* yraw, double* stats, float* coef, unsigned* cnt,
+                 float* oraw, float* lse, cudaStream_t st);
+
 struct LaunchPlan { int SPB, segw; size_t smem_attn; };
 
 static int pow2_floor(int x) { int p = 1; while (p * 2 <= x) p *= 2; return p; }
@@ -258,7 +262,14 @@ int axial_forward_launch(const Dims& m, const MtAxialParams& p, const float* x, 
     if (cudaMemsetAsync(saved + m.sv_stats, 0, m.sv_zero_bytes, st) != cudaSuccess) return -1;
   }
   if (mask & 1) nl += launch_proj(m, p, x, yraw, stats, coef, cnt, st);
-  if (m.training && (mask & 2)) {
+  const bool v1 = (m.dbg & 2) != 0;        // MT_DEBUG_FLAGS bit1: force the v1 (one row per thread) kernels
+  int r2 = 0;
+  if (m.training && (mask & 2) && !v1) {
+    r2 = launch_attn2<0>(m, p, yraw, stats, coef, cnt, oraw, lse, st);
+    if (r2 < 0) return r2;
+    nl += r2;
+  }
+  if (m.training && (mask & 2) && r2 == 0) {
     LaunchPlan pl = plan_attn(m, 0, 48);
     if (pl.smem_attn > 227 * 1024) return -2;
 #define CALL_SIM(DD, PP)                                                                       \
@@ -268,7 +279,13 @@ int axial_forward_launch(const Dims& m, const MtAxialParams& p, const float* x, 
 #undef CALL_SIM
     ++nl;
   }
-  if (mask & 4) {
+  r2 = 0;
+  if ((mask & 4) && !v1) {
+    r2 = launch_attn2<1>(m, p, yraw, stats, coef, cnt, oraw, lse, st);
+    if (r2 < 0) return r2;
+    nl += r2;
+  }
+  if ((mask & 4) && r2 == 0) {
     LaunchPlan pl = plan_attn(m, 0, 24 + 2 * m.no * m.C);
     if (pl.smem_attn > 227 * 1024) return -2;
 #define CALL_ATTN(DD, PP)                                                                      \

@@ -53,7 +53,7 @@ static inline bool make_dims(const MtAxialDesc* d, Dims& m) {
   m.no = m.pos ? 2 : 1;
   { double n1 = (double)m.Bg * m.L, n2 = n1 * m.L; m.inv_n1 = 1.0 / n1; m.inv_n2 = 1.0 / n2;
     m.unb1 = n1 > 1 ? (float)(n1 / (n1 - 1.0)) : 1.f; m.unb2 = n2 > 1 ? (float)(n2 / (n2 - 1.0)) : 1.f; }
-  m.LP = (m.L % 32 == 0) ? m.L : m.L + 1;      // odd-ish pitch kills bank conflicts when a warp spans heads
+  m.LP = (m.L % 32 == 0) ? m.L : m.L + 4;      // padded pitch (16-byte aligned rows) spreads heads over banks when a warp spans heads
   int C = m.C;
   m.f_qkv_sum = 0; m.f_qkv_sq = 2 * C;
   m.f_sim_sum = 4 * C; m.f_sim_sq = 4 * C + m.nt * MT_G;
