@@ -58,9 +58,21 @@ __host__ __device__ __forceinline__ int rel_pitch(int L) { return 2 * L + 8; }
 // stage `relative` (2gp rows x (2L-1)) into smem twice: plain T[m] and shifted Ts[m+1]
 __device__ __forceinline__ void load_rel2(const Dims& m, const float* __restrict__ rel, float* Rp, float* Rs) {
   const int RP = rel_pitch(m.L), RL = 2 * m.L - 1, rows = 2 * m.gp;
-  for (int idx = threadIdx.x; idx < rows * RP; idx += blockDim.x) {
-    const int c = idx / RP, x = idx - c * RP;
-    Rp[idx] = x < RL ? __ldg(rel + c * RL + x) : 0.f;
-    Rs[idx] = (x >= 1 && x <= RL) ? __ldg(rel + c * RL + x - 1) : 0.f;
+  for (int x = threadIdx.x; x < RP; x += blockDim.x) {
+    const bool in0 = x < RL, in1 = x >= 1 && x <= RL;
+    for (int c0 = 0; c0 < rows; c0 += 8) {          // 8 rows per batch: 16 independent loads in flight
+      float a[8], b[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = c0 + k;
+        a[k] = (in0 && c < rows) ? __ldg(rel + c * RL + x) : 0.f;
+        b[k] = (in1 && c < rows) ? __ldg(rel + c * RL + x - 1) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = c0 + k;
+        if (c < rows) { Rp[c * RP + x] = a[k]; Rs[c * RP + x] = b[k]; }
+      }
+    }
   }
 }

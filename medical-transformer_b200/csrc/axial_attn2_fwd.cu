@@ -30,14 +30,7 @@ k_attn2(Dims m, MtAxialParams p, const float* __restrict__ yraw, double* __restr
   for (int k = threadIdx.x; k < nred; k += blockDim.x) red[k] = 0.f;
   if (POS) load_rel2(m, p.relative, Rp, Rs);
   __syncthreads();
-  {
-    const int per = 2 * C * L;
-    const float* src = yraw + (size_t)b0 * per;
-    for (int idx = threadIdx.x; idx < SPB * per; idx += blockDim.x) {
-      const int s = idx / per, rem = idx - s * per, ch = rem / L, l = rem - ch * L;
-      Yn[((size_t)s * 2 * C + ch) * LP + l] = fmaf(ca[ch], __ldg(src + idx), cb[ch]);
-    }
-  }
+  stage_rows(yraw + (size_t)b0 * 2 * C * L, SPB * 2 * C, L, LP, ca, cb, 2 * C, Yn);
   __syncthreads();
 
   const int nitems = SPB * MT_G * LB;

@@ -65,23 +65,32 @@ __device__ __forceinline__ void bwd_load(const Dims& m, const MtAxialParams& p, 
     for (int idx = threadIdx.x; idx < nrel; idx += blockDim.x) s.R[idx] = __ldg(p.relative + idx);
   }
   __syncthreads();
+  stage_rows(yraw + (size_t)b0 * 2 * C * L, SPB * 2 * C, L, LP, s.ca, s.cb, 2 * C, s.Yn);
   {
-    const int per = 2 * C * L;
-    const float* src = yraw + (size_t)b0 * per;
-    for (int idx = threadIdx.x; idx < SPB * per; idx += blockDim.x) {
-      int ss = idx / per, rem = idx - ss * per;
-      int ch = rem / L, l = rem - ch * L;
-      s.Yn[((size_t)ss * 2 * C + ch) * LP + l] = fmaf(s.ca[ch], __ldg(src + idx), s.cb[ch]);
-    }
-  }
-  {
+    // dO = oA * g_s + oC * o_raw + oB, staged with batched loads (two sources per element)
     const int per = NOC * L;
     const float* src = oraw + (size_t)b0 * per;
-    for (int idx = threadIdx.x; idx < SPB * per; idx += blockDim.x) {
-      int ss = idx / per, rem = idx - ss * per;
-      int ch = rem / L, l = rem - ch * L;
-      float g = __ldg(gs + ((size_t)(b0 + ss) * C + ch / NO) * L + l);
-      s.dOs[((size_t)ss * NOC + ch) * LP + l] = fmaf(s.oA[ch], g, fmaf(s.oC[ch], __ldg(src + idx), s.oB[ch]));
+    constexpr int U = 4;
+    for (int base = 0; base < SPB * per; base += U * blockDim.x) {
+      float vo[U], vg[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int idx = base + u * blockDim.x + threadIdx.x;
+        vo[u] = 0.f; vg[u] = 0.f;
+        if (idx < SPB * per) {
+          const int ss = idx / per, rem = idx - ss * per, ch = rem / L, l = rem - ch * L;
+          vo[u] = __ldg(src + idx);
+          vg[u] = __ldg(gs + ((size_t)(b0 + ss) * C + ch / NO) * L + l);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int idx = base + u * blockDim.x + threadIdx.x;
+        if (idx < SPB * per) {
+          const int ss = idx / per, rem = idx - ss * per, ch = rem / L, l = rem - ch * L;
+          s.dOs[((size_t)ss * NOC + ch) * LP + l] = fmaf(s.oA[ch], vg[u], fmaf(s.oC[ch], vo[u], s.oB[ch]));
+        }
+      }
     }
     for (int idx = threadIdx.x; idx < SPB * MT_G * L; idx += blockDim.x)
       s.lses[idx] = __ldg(lse + (size_t)b0 * MT_G * L + idx);
@@ -94,7 +103,13 @@ __device__ __forceinline__ void bwd_load(const Dims& m, const MtAxialParams& p, 
       const float* o = oraw + (size_t)(b0 + ss) * per + (size_t)g * gpn * L + i;
       const float* dO = s.dOs + ((size_t)ss * NOC + g * gpn) * LP + i;
       float acc = 0.f;
-      for (int k = 0; k < gpn; ++k) acc = fmaf(dO[(size_t)k * LP], __ldg(o + (size_t)k * L), acc);
+      for (int k0 = 0; k0 < gpn; k0 += 8) {
+        float ov[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ov[k] = (k0 + k < gpn) ? __ldg(o + (size_t)(k0 + k) * L) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (k0 + k < gpn) acc = fmaf(dO[(size_t)(k0 + k) * LP], ov[k], acc);
+      }
       s.Dl[idx] = acc;
     }
   }

@@ -23,13 +23,7 @@ __device__ __forceinline__ void load_qkv_coef(const Dims& m, const float* __rest
 // normalised q,k,v strips of `spb` consecutive strips starting at b0 -> Yn[s][ch][LP]
 __device__ __forceinline__ void load_strips_norm(const Dims& m, const float* __restrict__ yraw, int b0, int spb,
                                                  const float* ca, const float* cb, float* Yn) {
-  const int per = 2 * m.C * m.L;
-  const float* src = yraw + (size_t)b0 * per;
-  for (int idx = threadIdx.x; idx < spb * per; idx += blockDim.x) {
-    int s = idx / per, rem = idx - s * per;
-    int ch = rem / m.L, l = rem - ch * m.L;
-    Yn[((size_t)s * 2 * m.C + ch) * m.LP + l] = fmaf(ca[ch], __ldg(src + idx), cb[ch]);
-  }
+  stage_rows(yraw + (size_t)b0 * 2 * m.C * m.L, spb * 2 * m.C, m.L, m.LP, ca, cb, 2 * m.C, Yn);
 }
 
 __device__ __forceinline__ void load_rel(const Dims& m, const float* __restrict__ rel, float* R) {

@@ -383,3 +383,49 @@ __device__ __forceinline__ void bwd_param_grads(const Dims& m, const MtAxialPara
     gr.dgates[tid] = t;
   }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Batched staging.  ncu (profiles/r1_notes.md): the first kernels spent most of their cycles in
+// "long scoreboard" stalls because global->shared staging loops did load -> use -> store one
+// element at a time (16-64 serialised L2 round trips per thread).  These helpers issue U
+// independent 16-byte loads per thread before touching any of them.
+//
+// rows [nrows][L] contiguous in global (L % 4 == 0, 16-byte aligned) -> dst[row][LP], with the
+// per-row affine a[row % ncoef] * x + b[row % ncoef].
+template <int U>
+__device__ __forceinline__ void stage_rows_affine(const float* __restrict__ src, int nrows, int L, int LP,
+                                                  const float* a, const float* b, int ncoef, float* dst) {
+  const int L4 = L >> 2, total4 = nrows * L4;
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  for (int base = 0; base < total4; base += U * blockDim.x) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i4 = base + u * blockDim.x + threadIdx.x;
+      v[u] = i4 < total4 ? __ldg(s4 + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i4 = base + u * blockDim.x + threadIdx.x;
+      if (i4 < total4) {
+        const int row = i4 / L4, l = (i4 - row * L4) << 2, rc = row % ncoef;
+        const float ka = a[rc], kb = b[rc];
+        float4 o = make_float4(fmaf(ka, v[u].x, kb), fmaf(ka, v[u].y, kb), fmaf(ka, v[u].z, kb), fmaf(ka, v[u].w, kb));
+        *reinterpret_cast<float4*>(dst + (size_t)row * LP + l) = o;
+      }
+    }
+  }
+}
+// scalar fallback (L % 4 != 0)
+__device__ __forceinline__ void stage_rows_affine_scalar(const float* __restrict__ src, int nrows, int L, int LP,
+                                                         const float* a, const float* b, int ncoef, float* dst) {
+  for (int idx = threadIdx.x; idx < nrows * L; idx += blockDim.x) {
+    const int row = idx / L, l = idx - row * L, rc = row % ncoef;
+    dst[(size_t)row * LP + l] = fmaf(a[rc], __ldg(src + idx), b[rc]);
+  }
+}
+__device__ __forceinline__ void stage_rows(const float* __restrict__ src, int nrows, int L, int LP, const float* a,
+                                           const float* b, int ncoef, float* dst) {
+  if ((L & 3) == 0 && (LP & 3) == 0) stage_rows_affine<4>(src, nrows, L, LP, a, b, ncoef, dst);
+  else stage_rows_affine_scalar(src, nrows, L, LP, a, b, ncoef, dst);
+}

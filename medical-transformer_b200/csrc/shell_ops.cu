@@ -111,21 +111,43 @@ __device__ __forceinline__ float2 block_sum2(float a, float b) {
   return make_float2(sa, sb);
 }
 
+// element i4 (float4 index inside the (group, channel) slab) -> global float4 offset
+__device__ __forceinline__ size_t bn_off4(const BnActArgs& a, int g, int c, int npg, int hw4, int i4) {
+  const int n = i4 / hw4, r = i4 - n * hw4;
+  return ((size_t)(g * npg + n) * a.C + c) * hw4 + r;
+}
+
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 k_bn_act_fwd(BnActArgs a, const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ gamma,
              const float* __restrict__ beta, float* __restrict__ rm, float* __restrict__ rv, float* __restrict__ y,
              float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  constexpr int U = 4, W = VEC ? 4 : 1;
   const int c = blockIdx.x, g = blockIdx.y;
-  const int npg = a.N / a.G, cnt = npg * a.HW;
+  const int npg = a.N / a.G, hw4 = a.HW / W, cnt4 = npg * hw4, cnt = npg * a.HW;
   float mean, invstd;
   if (a.training) {
     // pass 1: shifted sums (shift = first element) keep the fp32 variance well conditioned
     const float shift = __ldg(x + ((size_t)(g * npg) * a.C + c) * a.HW);
     float s1 = 0.f, s2 = 0.f;
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-      const int n = i / a.HW, r = i - n * a.HW;
-      const float v = __ldg(x + ((size_t)(g * npg + n) * a.C + c) * a.HW + r) - shift;
-      s1 += v; s2 = fmaf(v, v, s2);
+    for (int base = 0; base < cnt4; base += U * blockDim.x) {
+      float v[U][W];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i4 = base + u * blockDim.x + threadIdx.x;
+        if (i4 < cnt4) {
+          if (VEC) { const float4 t = __ldg(reinterpret_cast<const float4*>(x) + bn_off4(a, g, c, npg, hw4, i4));
+                     v[u][0] = t.x; v[u][W > 1 ? 1 : 0] = t.y; v[u][W > 2 ? 2 : 0] = t.z; v[u][W > 3 ? 3 : 0] = t.w; }
+          else v[u][0] = __ldg(x + bn_off4(a, g, c, npg, hw4, i4));
+        } else {
+#pragma unroll
+          for (int k = 0; k < W; ++k) v[u][k] = shift;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int k = 0; k < W; ++k) { const float d = v[u][k] - shift; s1 += d; s2 = fmaf(d, d, s2); }
     }
     const float2 s = block_sum2(s1, s2);
     const float inv_n = 1.f / (float)cnt;
@@ -143,13 +165,41 @@ k_bn_act_fwd(BnActArgs a, const float* __restrict__ x, const float* __restrict__
     if (threadIdx.x == 0) { save_mean[g * a.C + c] = mean; save_invstd[g * a.C + c] = invstd; }
   }
   const float ga = gamma[c] * invstd, be = beta[c] - mean * ga;
-  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-    const int n = i / a.HW, r = i - n * a.HW;
-    const size_t o = ((size_t)(g * npg + n) * a.C + c) * a.HW + r;
-    float v = fmaf(ga, __ldg(x + o), be);
-    if (res) v += __ldg(res + o);
-    if (a.relu) v = v > 0.f ? v : 0.f;
-    y[o] = v;
+  for (int base = 0; base < cnt4; base += U * blockDim.x) {
+    float v[U][W], rr[U][W];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i4 = base + u * blockDim.x + threadIdx.x;
+#pragma unroll
+      for (int k = 0; k < W; ++k) { v[u][k] = 0.f; rr[u][k] = 0.f; }
+      if (i4 < cnt4) {
+        const size_t o = bn_off4(a, g, c, npg, hw4, i4);
+        if (VEC) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(x) + o);
+          v[u][0] = t.x; v[u][W > 1 ? 1 : 0] = t.y; v[u][W > 2 ? 2 : 0] = t.z; v[u][W > 3 ? 3 : 0] = t.w;
+          if (res) { const float4 q = __ldg(reinterpret_cast<const float4*>(res) + o);
+                     rr[u][0] = q.x; rr[u][W > 1 ? 1 : 0] = q.y; rr[u][W > 2 ? 2 : 0] = q.z; rr[u][W > 3 ? 3 : 0] = q.w; }
+        } else {
+          v[u][0] = __ldg(x + o);
+          if (res) rr[u][0] = __ldg(res + o);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i4 = base + u * blockDim.x + threadIdx.x;
+      if (i4 < cnt4) {
+        float o4[W];
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+          float t = fmaf(ga, v[u][k], be) + rr[u][k];
+          o4[k] = (a.relu && !(t > 0.f)) ? 0.f : t;
+        }
+        const size_t o = bn_off4(a, g, c, npg, hw4, i4);
+        if (VEC) reinterpret_cast<float4*>(y)[o] = make_float4(o4[0], o4[W > 1 ? 1 : 0], o4[W > 2 ? 2 : 0], o4[W > 3 ? 3 : 0]);
+        else y[o] = o4[0];
+      }
+    }
   }
 }
 
@@ -168,20 +218,44 @@ __global__ void k_bn_ema(BnActArgs a, const float* __restrict__ save_mean, float
 }
 
 // dx (and d residual = masked dy), dgamma / dbeta accumulated over groups
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 k_bn_act_bwd(BnActArgs a, const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dy,
              const float* __restrict__ gamma, const float* __restrict__ save_mean, const float* __restrict__ save_invstd,
              float* __restrict__ dx, float* __restrict__ dres, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  constexpr int U = 4, W = VEC ? 4 : 1;
   const int c = blockIdx.x, g = blockIdx.y;
-  const int npg = a.N / a.G, cnt = npg * a.HW;
+  const int npg = a.N / a.G, hw4 = a.HW / W, cnt4 = npg * hw4, cnt = npg * a.HW;
   const float mean = save_mean[g * a.C + c], invstd = save_invstd[g * a.C + c];
   float s1 = 0.f, s2 = 0.f;
-  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-    const int n = i / a.HW, r = i - n * a.HW;
-    const size_t o = ((size_t)(g * npg + n) * a.C + c) * a.HW + r;
-    float d = __ldg(dy + o);
-    if (a.relu && !(__ldg(y + o) > 0.f)) d = 0.f;
-    s1 += d; s2 = fmaf(d, (__ldg(x + o) - mean) * invstd, s2);
+  for (int base = 0; base < cnt4; base += U * blockDim.x) {
+    float vx[U][W], vy[U][W], vd[U][W];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i4 = base + u * blockDim.x + threadIdx.x;
+#pragma unroll
+      for (int k = 0; k < W; ++k) { vx[u][k] = mean; vy[u][k] = 1.f; vd[u][k] = 0.f; }
+      if (i4 < cnt4) {
+        const size_t o = bn_off4(a, g, c, npg, hw4, i4);
+        if (VEC) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(x) + o), d = __ldg(reinterpret_cast<const float4*>(dy) + o);
+          vx[u][0] = t.x; vx[u][W > 1 ? 1 : 0] = t.y; vx[u][W > 2 ? 2 : 0] = t.z; vx[u][W > 3 ? 3 : 0] = t.w;
+          vd[u][0] = d.x; vd[u][W > 1 ? 1 : 0] = d.y; vd[u][W > 2 ? 2 : 0] = d.z; vd[u][W > 3 ? 3 : 0] = d.w;
+          if (a.relu) { const float4 q = __ldg(reinterpret_cast<const float4*>(y) + o);
+                        vy[u][0] = q.x; vy[u][W > 1 ? 1 : 0] = q.y; vy[u][W > 2 ? 2 : 0] = q.z; vy[u][W > 3 ? 3 : 0] = q.w; }
+        } else {
+          vx[u][0] = __ldg(x + o); vd[u][0] = __ldg(dy + o);
+          if (a.relu) vy[u][0] = __ldg(y + o);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        const float d = (a.relu && !(vy[u][k] > 0.f)) ? 0.f : vd[u][k];
+        s1 += d; s2 = fmaf(d, (vx[u][k] - mean) * invstd, s2);
+      }
   }
   const float2 s = block_sum2(s1, s2);
   if (threadIdx.x == 0) {
@@ -190,14 +264,47 @@ k_bn_act_bwd(BnActArgs a, const float* __restrict__ x, const float* __restrict__
   }
   const float ga = gamma[c] * invstd, inv_n = 1.f / (float)cnt;
   const float m1 = a.training ? s.x * inv_n : 0.f, m2 = a.training ? s.y * inv_n : 0.f;
-  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-    const int n = i / a.HW, r = i - n * a.HW;
-    const size_t o = ((size_t)(g * npg + n) * a.C + c) * a.HW + r;
-    float d = __ldg(dy + o);
-    if (a.relu && !(__ldg(y + o) > 0.f)) d = 0.f;
-    if (dres) dres[o] = d;
-    const float xh = (__ldg(x + o) - mean) * invstd;
-    dx[o] = ga * (d - m1 - xh * m2);
+  for (int base = 0; base < cnt4; base += U * blockDim.x) {
+    float vx[U][W], vy[U][W], vd[U][W];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i4 = base + u * blockDim.x + threadIdx.x;
+#pragma unroll
+      for (int k = 0; k < W; ++k) { vx[u][k] = mean; vy[u][k] = 1.f; vd[u][k] = 0.f; }
+      if (i4 < cnt4) {
+        const size_t o = bn_off4(a, g, c, npg, hw4, i4);
+        if (VEC) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(x) + o), d = __ldg(reinterpret_cast<const float4*>(dy) + o);
+          vx[u][0] = t.x; vx[u][W > 1 ? 1 : 0] = t.y; vx[u][W > 2 ? 2 : 0] = t.z; vx[u][W > 3 ? 3 : 0] = t.w;
+          vd[u][0] = d.x; vd[u][W > 1 ? 1 : 0] = d.y; vd[u][W > 2 ? 2 : 0] = d.z; vd[u][W > 3 ? 3 : 0] = d.w;
+          if (a.relu) { const float4 q = __ldg(reinterpret_cast<const float4*>(y) + o);
+                        vy[u][0] = q.x; vy[u][W > 1 ? 1 : 0] = q.y; vy[u][W > 2 ? 2 : 0] = q.z; vy[u][W > 3 ? 3 : 0] = q.w; }
+        } else {
+          vx[u][0] = __ldg(x + o); vd[u][0] = __ldg(dy + o);
+          if (a.relu) vy[u][0] = __ldg(y + o);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i4 = base + u * blockDim.x + threadIdx.x;
+      if (i4 < cnt4) {
+        float od[W], ox[W];
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+          od[k] = (a.relu && !(vy[u][k] > 0.f)) ? 0.f : vd[u][k];
+          ox[k] = ga * (od[k] - m1 - (vx[u][k] - mean) * invstd * m2);
+        }
+        const size_t o = bn_off4(a, g, c, npg, hw4, i4);
+        if (VEC) {
+          reinterpret_cast<float4*>(dx)[o] = make_float4(ox[0], ox[W > 1 ? 1 : 0], ox[W > 2 ? 2 : 0], ox[W > 3 ? 3 : 0]);
+          if (dres) reinterpret_cast<float4*>(dres)[o] = make_float4(od[0], od[W > 1 ? 1 : 0], od[W > 2 ? 2 : 0], od[W > 3 ? 3 : 0]);
+        } else {
+          dx[o] = ox[0];
+          if (dres) dres[o] = od[0];
+        }
+      }
+    }
   }
 }
 
@@ -234,10 +341,14 @@ int mt_bn_act_forward(int N, int C, int HW, int groups, int training, int relu, 
     return mt_fail_msg(MT_ERR_BAD_ARG, "mt_bn_act_forward: bad argument");
   if (training && (long)(N / groups) * HW < 2) return mt_fail_msg(MT_ERR_BAD_ARG, "mt_bn_act_forward: training needs more than one value per channel");
   BnActArgs a{N, C, HW, groups, training, relu, eps, momentum};
-  const int cnt = (N / groups) * HW;
-  const int bs = cnt >= 256 ? 256 : (cnt >= 128 ? 128 : 64);
-  k_bn_act_fwd<<<dim3(C, groups), bs, 0, (cudaStream_t)stream>>>(a, x, residual, gamma, beta, running_mean, running_var, y,
-                                                                   save_mean, save_invstd);
+  const int cnt = (N / groups) * HW / (HW % 4 == 0 ? 4 : 1);
+  const int bs = cnt >= 1024 ? 256 : (cnt >= 256 ? 128 : 64);
+  if (HW % 4 == 0)
+    k_bn_act_fwd<true><<<dim3(C, groups), bs, 0, (cudaStream_t)stream>>>(a, x, residual, gamma, beta, running_mean,
+                                                                           running_var, y, save_mean, save_invstd);
+  else
+    k_bn_act_fwd<false><<<dim3(C, groups), bs, 0, (cudaStream_t)stream>>>(a, x, residual, gamma, beta, running_mean,
+                                                                            running_var, y, save_mean, save_invstd);
   if (training) k_bn_ema<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a, save_mean, running_mean, running_var);
   g_last_cuda = cudaGetLastError();
   return g_last_cuda == cudaSuccess ? MT_OK : mt_fail_msg(MT_ERR_CUDA, "mt_bn_act_forward: launch failed");
@@ -254,10 +365,14 @@ int mt_bn_act_backward(int N, int C, int HW, int groups, int training, int relu,
     cudaMemsetAsync(dgamma, 0, sizeof(float) * C, (cudaStream_t)stream);
     cudaMemsetAsync(dbeta, 0, sizeof(float) * C, (cudaStream_t)stream);
   }
-  const int cnt = (N / groups) * HW;
-  const int bs = cnt >= 256 ? 256 : (cnt >= 128 ? 128 : 64);
-  k_bn_act_bwd<<<dim3(C, groups), bs, 0, (cudaStream_t)stream>>>(a, x, y, dy, gamma, save_mean, save_invstd, dx, dresidual,
-                                                                   dgamma, dbeta);
+  const int cnt = (N / groups) * HW / (HW % 4 == 0 ? 4 : 1);
+  const int bs = cnt >= 1024 ? 256 : (cnt >= 256 ? 128 : 64);
+  if (HW % 4 == 0)
+    k_bn_act_bwd<true><<<dim3(C, groups), bs, 0, (cudaStream_t)stream>>>(a, x, y, dy, gamma, save_mean, save_invstd, dx,
+                                                                           dresidual, dgamma, dbeta);
+  else
+    k_bn_act_bwd<false><<<dim3(C, groups), bs, 0, (cudaStream_t)stream>>>(a, x, y, dy, gamma, save_mean, save_invstd, dx,
+                                                                            dresidual, dgamma, dbeta);
   g_last_cuda = cudaGetLastError();
   return g_last_cuda == cudaSuccess ? MT_OK : mt_fail_msg(MT_ERR_CUDA, "mt_bn_act_backward: launch failed");
 }
