@@ -25,6 +25,39 @@ import torch.distributed as dist
 import torch.nn.functional as F
 
 
+class FlatBucket:
+    """ONE flat gradient bucket for data-parallel training: gather the per-parameter gradients
+    with a single `torch.cat`, all-reduce (mean) once, hand the averaged views back.  Pure
+    torch / torch.distributed, device agnostic (NCCL on GPUs; the gloo CPU test uses it too)."""
+
+    def __init__(self, params, process_group=None):
+        self.params = list(params)
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        total = sum(p.numel() for p in self.params)
+        dev = self.params[0].device if self.params else "cpu"
+        self.flat = torch.zeros(total, device=dev)
+        self.views, off = [], 0
+        for p in self.params:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+
+    def nbytes(self):
+        return self.flat.numel() * self.flat.element_size()
+
+    def reduce_(self):
+        """p.grad (fresh autograd tensors) -> bucket -> mean over ranks -> p.grad = bucket views."""
+        torch.cat([p.grad.reshape(-1) for p in self.params], out=self.flat)
+        if self.world > 1:
+            if dist.get_backend(self.pg) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.pg)
+            else:                                   # gloo has no AVG
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.pg)
+                self.flat.div_(self.world)
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+
 class TrainStep:
     def __init__(self, model, batch_shape, lr=1e-3, weight_decay=1e-5, device=None, use_graph=True,
                  process_group=None, loss_slots=64):
@@ -72,15 +105,7 @@ class TrainStep:
             b._nbt_deferred = True
         self.active = self._probe_active_params()          # its forward records each BN's statistic-group count
         self._nbt_inc = torch.tensor([int(getattr(b, "_stat_groups_bn", 1)) for b in bns], device=self.device)
-        total = sum(p.numel() for p in self.active)
-        self.flat_grad = torch.zeros(total, device=self.device) if self.world > 1 else None
-        self._grad_views = None
-        if self.world > 1:
-            off, views = 0, []
-            for p in self.active:                   # views of the single all-reduce bucket
-                views.append(self.flat_grad[off:off + p.numel()].view_as(p))
-                off += p.numel()
-            self._grad_views = views
+        self.bucket = FlatBucket(self.active, self.pg) if self.world > 1 else None
         old_state = self.opt.state_dict() if self.opt is not None else None
         self.opt = torch.optim.Adam(self.active, lr=self.lr, weight_decay=self.weight_decay, capturable=True,
                                     fused=True)
@@ -126,11 +151,8 @@ class TrainStep:
         out = self.model(self.x)
         loss = F.cross_entropy(out, self.y)                    # LogNLLLoss == cross_entropy (metrics.py:17-20)
         loss.backward()
-        if self.world > 1:
-            torch.cat([p.grad.reshape(-1) for p in self.active], out=self.flat_grad)
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG, group=self.pg)
-            for p, v in zip(self.active, self._grad_views):
-                p.grad = v
+        if self.bucket is not None:
+            self.bucket.reduce_()
         self.opt.step()
         if self._nbt is not None:
             self._nbt += self._nbt_inc

@@ -1,0 +1,90 @@
+"""CPU tier, world_size 2 over gloo: the host logic of the data-parallel step --
+ONE flat gradient bucket, mean all-reduce, gradients handed back as views, parameters without
+gradients left out -- followed by an optimizer step that must keep both ranks bit-identical."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from medt_b200.train_step import FlatBucket
+        torch.manual_seed(0)                                   # identical replicas
+        net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3, padding=1), torch.nn.BatchNorm2d(4), torch.nn.ReLU(),
+                                  torch.nn.Conv2d(4, 2, 1))
+        frozen = torch.nn.Parameter(torch.tensor(0.1), requires_grad=False)   # like the gates before epoch 10
+        params = [p for p in list(net.parameters()) + [frozen] if p.requires_grad]
+        opt = torch.optim.Adam(params, lr=1e-2, weight_decay=1e-5)
+        bucket = FlatBucket(params)
+        assert bucket.world == world and bucket.nbytes() == 4 * sum(p.numel() for p in params)
+        torch.manual_seed(100 + rank)                          # different data shard per rank
+        x, y = torch.rand(4, 3, 8, 8), torch.randint(0, 2, (4, 8, 8))
+        for p in params:
+            p.grad = None
+        torch.nn.functional.cross_entropy(net(x), y).backward()
+        local = [p.grad.clone() for p in params]
+        bucket.reduce_()
+        gathered = [torch.zeros_like(torch.cat([g.reshape(-1) for g in local])) for _ in range(world)]
+        dist.all_gather(gathered, torch.cat([g.reshape(-1) for g in local]))
+        mean = sum(gathered) / world
+        assert torch.allclose(bucket.flat, mean, atol=1e-7)
+        assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, bucket.views))   # views, no copies
+        opt.step()
+        flat_p = torch.cat([p.detach().reshape(-1) for p in params])
+        both = [torch.zeros_like(flat_p) for _ in range(world)]
+        dist.all_gather(both, flat_p)
+        assert torch.equal(both[0], both[1])                   # replicas stay in lock-step
+        # BN statistics stay per rank (DataParallel semantics of the reference, no SyncBN)
+        rm = net[1].running_mean.clone()
+        rms = [torch.zeros_like(rm) for _ in range(world)]
+        dist.all_gather(rms, rm)
+        assert not torch.equal(rms[0], rms[1])
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_bucket_allreduce_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_reference_script_launcher_paths(tmp_path, monkeypatch):
+    """run_reference_script.py: the drop-in `lib` must win over the reference's, while the script's
+    bare `import utils / metrics` still resolve in the reference directory."""
+    import importlib.util
+    import sys
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("rrs", os.path.join(here, "medical-transformer_b200", "run_reference_script.py"))
+    rrs = importlib.util.module_from_spec(spec); spec.loader.exec_module(rrs)
+    ref = tmp_path / "Medical-Transformer"; (ref / "lib").mkdir(parents=True)
+    (ref / "lib" / "__init__.py").write_text("WHO = 'reference'\n"); (ref / "metrics.py").write_text("WHO = 'reference'\n")
+    (ref / "train.py").write_text("")
+    monkeypatch.setattr(sys, "path", [str(ref)] + list(sys.path))
+    pkg, ref_dir = rrs.setup_paths(str(ref / "train.py"))
+    assert sys.path[0] == pkg and sys.path.index(ref_dir) > 0
+    for m in ("lib", "metrics"):
+        sys.modules.pop(m, None)
+    import lib, metrics  # noqa: E401
+    assert not hasattr(lib, "WHO") and lib.__file__.startswith(pkg) and metrics.WHO == "reference"
+    sys.modules.pop("metrics", None)
