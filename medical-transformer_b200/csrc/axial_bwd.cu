@@ -209,6 +209,9 @@ k_bwd_attn(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ 
   const int C = m.C, L = m.L, LP = m.LP, NO = m.no, NOC = NO * C, RL = 2 * L - 1;
   const int b0 = blockIdx.x * SPB, grp = b0 / m.Bg;
   const int nrel = POS ? 2 * GP * RL : 0;
+  // the three passes are independent given the staged strip: blockIdx.y picks one, so they run
+  // on different SMs concurrently (rows -> dq, columns -> dk/dv, diagonals -> d relative)
+  const int phase = blockIdx.y;
   BwdSmem s = carve(m, sm, SPB, 4 * C + nrel);      // red: [2C][2] qkv sums, then dR accumulators
   float* dRs = s.red + 4 * C;
   for (int k = threadIdx.x; k < 4 * C + nrel; k += blockDim.x) s.red[k] = 0.f;
@@ -216,6 +219,7 @@ k_bwd_attn(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ 
   const int nitems = SPB * MT_G * L;
 
   // ---- rows: dq[c,i] = sum_j dS_qk k[c,j] + dS_qr Rq[c,i-j]
+  if (phase == 0)
   for (int base = 0; base < nitems; base += blockDim.x) {
     const int item = base + threadIdx.x;
     const bool act = item < nitems;
@@ -254,6 +258,7 @@ k_bwd_attn(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ 
   }
 
   // ---- columns: dk[c,j] = sum_i dS_qk q[c,i] + dS_kr Rk[c,j-i] ; dv[c,j] = sum_i P dO_sv[c,i]
+  if (phase == 1)
   for (int base = 0; base < nitems; base += blockDim.x) {
     const int item = base + threadIdx.x;
     const bool act = item < nitems;
@@ -299,7 +304,7 @@ k_bwd_attn(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ 
 
   // ---- diagonals: thread (s, g, mm) walks the pairs (i, j = i - mm + L - 1)
   //      dRq[c,mm] += dS_qr q[c,i] ; dRv[c,mm] += P dO_sve[c,i] ; dRk[c, 2(L-1)-mm] += dS_kr k[c,j]
-  if (POS) {
+  if (POS && phase == 2) {
     const int nd = SPB * MT_G * RL;
     for (int base = 0; base < nd; base += blockDim.x) {
       const int item = base + threadIdx.x;
@@ -344,14 +349,18 @@ k_bwd_attn(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ 
   }
   __syncthreads();
   double* bs = stat_slot(m, bstats, grp, m.nstat_b, blockIdx.x);
-  for (int ch = threadIdx.x; ch < 2 * C; ch += blockDim.x) {
-    MT_GADD(m, bs + m.b_qkv_s1 + ch, (double)s.red[ch * 2]);
-    MT_GADD(m, bs + m.b_qkv_s2 + ch, (double)s.red[ch * 2 + 1]);
-  }
-  if (POS)
+  if (phase < 2)
+    for (int ch = threadIdx.x; ch < 2 * C; ch += blockDim.x) {
+      const int r = ch % (2 * GP);                   // q rows belong to the row pass, k / v rows to the column pass
+      if ((r < D) == (phase == 0)) {
+        MT_GADD(m, bs + m.b_qkv_s1 + ch, (double)s.red[ch * 2]);
+        MT_GADD(m, bs + m.b_qkv_s2 + ch, (double)s.red[ch * 2 + 1]);
+      }
+    }
+  if (POS && phase == 2)
     for (int k = threadIdx.x; k < nrel; k += blockDim.x) MT_GADD(m, drel + k, dRs[k]);
   // last CTA: bn_qkv backward coefficients for the projection GEMMs + every BN / gate parameter gradient
-  if (last_cta_done(bcnt + 2, gridDim.x)) {
+  if (last_cta_done(bcnt + 2, gridDim.x * gridDim.y)) {
     fin_bwd_qkv(m, p, stats, bstats, bcoef);
     bwd_param_grads(m, p, gr, stats, bstats);
   }
@@ -424,7 +433,7 @@ int axial_backward_launch(const Dims& m, const MtAxialParams& p, const float* x,
     if (m.pos && !gr.drelative) return -3;
 #define CALL_BA(DD, PP)                                                                               \
     if (set_smem_b(k_bwd_attn<DD, PP>, smem) != cudaSuccess) return -1;                                 \
-    k_bwd_attn<DD, PP><<<m.B / spb, 256, smem, st>>>(m, p, gr, stats, bstats, coef, bcoef, bcnt, yraw, oraw, lse, \
+    k_bwd_attn<DD, PP><<<dim3(m.B / spb, PP ? 3 : 2), 256, smem, st>>>(m, p, gr, stats, bstats, coef, bcoef, bcnt, yraw, oraw, lse, \
                                                      gs, dyh, gr.drelative, spb, segw)
     MT_DISPATCH_DB(m, CALL_BA)
 #undef CALL_BA

@@ -71,6 +71,16 @@ k_proj(Dims m, MtAxialParams p, const float* __restrict__ x, const float* __rest
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   if (tid < 64) { red[tid][0] = 0.f; red[tid][1] = 0.f; }
+  const size_t plane = (size_t)m.H * m.W;
+  int xslot; bool xok; const float* xb;
+  {
+    const int r = tid & 63;
+    int s, l;
+    slot_x(m, t, r, s, l);
+    xok = slot_ok(m, t, r, s, l);
+    xslot = r < t.npos ? s * t.TL + l : r;
+    xb = x + (xok ? nchw_addr(m, t.grp * m.Bg + t.sb0 + s, 0, t.l0 + l) : 0);
+  }
   for (int k0 = 0; k0 < C; k0 += 16) {
     // A chunk: W[oc0 + mm][k0 + kk] -> As[kk][mm]   (each thread: one float4 of 4 consecutive k)
     {
@@ -80,16 +90,14 @@ k_proj(Dims m, MtAxialParams p, const float* __restrict__ x, const float* __rest
       As[(kq + 0) * TILE_LD + mm] = v.x; As[(kq + 1) * TILE_LD + mm] = v.y;
       As[(kq + 2) * TILE_LD + mm] = v.z; As[(kq + 3) * TILE_LD + mm] = v.w;
     }
-    // B chunk: X[k0 + kk][pos r] gathered from NCHW in x order, stored in strip order (l fastest)
+    // B chunk: X[k0 + kk][pos r] gathered from NCHW in x order, stored in strip order (l fastest).
+    // r = tid & 63 is the same for all four loads of this thread: address math hoisted (xb, xok, xslot)
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
-      const int idx = tid + it * 256, kk = idx >> 6, r = idx & 63;
-      int s, l;
-      slot_x(m, t, r, s, l);
+      const int kk = (tid >> 6) + 4 * it;
       float v = 0.f;
-      if (slot_ok(m, t, r, s, l) && k0 + kk < C)
-        v = __ldg(x + nchw_addr(m, t.grp * m.Bg + t.sb0 + s, k0 + kk, t.l0 + l));
-      if (r < t.npos) Bs[kk * TILE_LD + s * t.TL + l] = v; else Bs[kk * TILE_LD + r] = 0.f;
+      if (xok && k0 + kk < C) v = __ldg(xb + (size_t)(k0 + kk) * plane);
+      Bs[kk * TILE_LD + xslot] = v;
     }
     __syncthreads();
     mma_chunk(As, Bs, ty, tx, acc, C - k0 < 16 ? C - k0 : 16);
@@ -159,6 +167,12 @@ k_bwd_dx(Dims m, MtAxialParams p, MtAxialGrads gr, const float* __restrict__ bco
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  bool yok; size_t ybase;
+  {
+    const int r = tid & 63, s = r / t.TL, l = r - s * t.TL;
+    yok = r < t.npos && t.sb0 + s < m.Bg && t.l0 + l < m.L;
+    ybase = yok ? (size_t)(t.grp * m.Bg + t.sb0 + s) * K * m.L + t.l0 + l : 0;
+  }
   for (int k0 = 0; k0 < K; k0 += 16) {
     // A chunk: W^T: As[kk][mm] = W[k0+kk][c0+mm]  (row of W is contiguous in c)
     {
@@ -167,18 +181,21 @@ k_bwd_dx(Dims m, MtAxialParams p, MtAxialGrads gr, const float* __restrict__ bco
       if (k0 + kk < K && c0 + mq < C) v = __ldg(reinterpret_cast<const float4*>(p.w_qkv + (size_t)(k0 + kk) * C + c0 + mq));
       *reinterpret_cast<float4*>(As + kk * TILE_LD + mq) = v;
     }
-    // B chunk: dy_raw[k0+kk][pos] = A*dyh + Bc + Cc*yraw, strip order (contiguous TL-runs)
+    // B chunk: dy_raw[k0+kk][pos] = A*dyh + Bc + Cc*yraw, strip order (contiguous TL-runs); r = tid & 63 fixed
+    {
+      float vd[4], vy[4];
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int idx = tid + it * 256, kk = idx >> 6, r = idx & 63;
-      const int s = r / t.TL, l = r - s * t.TL;
-      float v = 0.f;
-      if (r < t.npos && t.sb0 + s < m.Bg && t.l0 + l < m.L && k0 + kk < K) {
-        const int ch = k0 + kk;
-        const size_t a = ((size_t)(t.grp * m.Bg + t.sb0 + s) * K + ch) * m.L + t.l0 + l;
-        v = fmaf(qA[ch], __ldg(dyh + a), fmaf(qC[ch], __ldg(yraw + a), qB[ch]));
+      for (int it = 0; it < 4; ++it) {
+        const int ch = k0 + (tid >> 6) + 4 * it;
+        const bool ok = yok && ch < K;
+        vd[it] = ok ? __ldg(dyh + ybase + (size_t)ch * m.L) : 0.f;
+        vy[it] = ok ? __ldg(yraw + ybase + (size_t)ch * m.L) : 0.f;
       }
-      Bs[kk * TILE_LD + r] = v;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int kk = (tid >> 6) + 4 * it, ch = k0 + kk;
+        Bs[kk * TILE_LD + (tid & 63)] = (yok && ch < K) ? fmaf(qA[ch], vd[it], fmaf(qC[ch], vy[it], qB[ch])) : 0.f;
+      }
     }
     __syncthreads();
     mma_chunk(As, Bs, ty, tx, acc, K - k0 < 16 ? K - k0 : 16);
@@ -191,13 +208,16 @@ k_bwd_dx(Dims m, MtAxialParams p, MtAxialGrads gr, const float* __restrict__ bco
     for (int j = 0; j < 4; ++j) Ts[(ty * 4 + i) * 65 + tx * 4 + j] = acc[i][j];
   __syncthreads();
   if (gr.dx) {
-    for (int idx = tid; idx < 64 * 64; idx += 256) {
-      const int cc = idx >> 6, r = idx & 63;
-      if (c0 + cc >= C || r >= t.npos) continue;
-      int s, l;
-      slot_x(m, t, r, s, l);
-      if (t.sb0 + s < m.Bg && t.l0 + l < m.L)
-        gr.dx[nchw_addr(m, t.grp * m.Bg + t.sb0 + s, c0 + cc, t.l0 + l)] = Ts[cc * 65 + s * t.TL + l];
+    const int r = tid & 63;
+    int s, l;
+    slot_x(m, t, r, s, l);
+    if (slot_ok(m, t, r, s, l)) {
+      float* dst = gr.dx + nchw_addr(m, t.grp * m.Bg + t.sb0 + s, 0, t.l0 + l);
+      const size_t plane = (size_t)m.H * m.W;
+      const int slot = s * t.TL + l;
+#pragma unroll 4
+      for (int cc = tid >> 6; cc < 64; cc += 4)
+        if (c0 + cc < C) dst[(size_t)(c0 + cc) * plane] = Ts[cc * 65 + slot];
     }
   }
 }
@@ -234,26 +254,35 @@ k_bwd_dw(Dims m, MtAxialGrads gr, const float* __restrict__ x, const float* __re
       cur_grp = t.grp;
       __syncthreads();
     }
-    // A: dy_raw[oc0+mm][pos r] -> Am[r][mm]  (strip order read, contiguous TL-runs)
-    for (int idx = tid; idx < 64 * 64; idx += 256) {
-      const int mm = idx >> 6, r = idx & 63;
-      const int s = r / t.TL, l = r - s * t.TL;
-      float v = 0.f;
-      if (r < t.npos && t.sb0 + s < m.Bg && t.l0 + l < m.L && oc0 + mm < M) {
-        const int ch = oc0 + mm;
-        const size_t a = ((size_t)(t.grp * m.Bg + t.sb0 + s) * M + ch) * m.L + t.l0 + l;
-        v = fmaf(qA[ch], __ldg(dyh + a), fmaf(qC[ch], __ldg(yraw + a), qB[ch]));
+    // A: dy_raw[oc0+mm][pos r] -> Am[r][mm]; B: X[c0+nn][pos r] -> Bm[slot][nn].  r = tid & 63 is fixed
+    // per thread, so all address math is done once per tile and 4 + 4 loads are issued back to back.
+    {
+      const int r = tid & 63, sy = r / t.TL, ly = r - sy * t.TL;
+      const bool yok = r < t.npos && t.sb0 + sy < m.Bg && t.l0 + ly < m.L;
+      const size_t ybase = yok ? (size_t)(t.grp * m.Bg + t.sb0 + sy) * M * m.L + t.l0 + ly : 0;
+      int sx, lx;
+      slot_x(m, t, r, sx, lx);
+      const bool xok = slot_ok(m, t, r, sx, lx);
+      const float* xb = x + (xok ? nchw_addr(m, t.grp * m.Bg + t.sb0 + sx, 0, t.l0 + lx) : 0);
+      const size_t plane = (size_t)m.H * m.W;
+      const int xslot = r < t.npos ? sx * t.TL + lx : r;
+      for (int m0 = tid >> 6; m0 < 64; m0 += 16) {
+        float vd[4], vy[4], vx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int mm = m0 + 4 * u, ch = oc0 + mm, cc = c0 + mm;
+          const bool oky = yok && ch < M, okx = xok && cc < C;
+          vd[u] = oky ? __ldg(dyh + ybase + (size_t)ch * m.L) : 0.f;
+          vy[u] = oky ? __ldg(yraw + ybase + (size_t)ch * m.L) : 0.f;
+          vx[u] = okx ? __ldg(xb + (size_t)cc * plane) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int mm = m0 + 4 * u, ch = oc0 + mm;
+          Am[r * TILE_LD + mm] = (yok && ch < M) ? fmaf(qA[ch], vd[u], fmaf(qC[ch], vy[u], qB[ch])) : 0.f;
+          Bm[xslot * TILE_LD + mm] = vx[u];
+        }
       }
-      Am[r * TILE_LD + mm] = v;
-    }
-    // B: X[c0+nn][pos] gathered in x order, stored at the strip-order slot
-    for (int idx = tid; idx < 64 * 64; idx += 256) {
-      const int nn = idx >> 6, r = idx & 63;
-      int s, l;
-      slot_x(m, t, r, s, l);
-      float v = 0.f;
-      if (slot_ok(m, t, r, s, l) && c0 + nn < C) v = __ldg(x + nchw_addr(m, t.grp * m.Bg + t.sb0 + s, c0 + nn, t.l0 + l));
-      if (r < t.npos) Bm[(s * t.TL + l) * TILE_LD + nn] = v; else Bm[r * TILE_LD + nn] = 0.f;
     }
     __syncthreads();
 #pragma unroll
