@@ -367,6 +367,10 @@ k_bwd_attn(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ 
 }
 
 // ============================================================================ host launcher
+template <int MODE>
+int launch_bwd2(const Dims& m, const MtAxialParams& p, const MtAxialGrads& gr, const double* stats, double* bstats,
+                const float* coef, float* bcoef, unsigned* bcnt, const float* yraw, const float* oraw, const float* lse,
+                const float* gs, float* dyh, cudaStream_t st);
 int launch_bwd_gather(const Dims& m, const MtAxialParams& p, const float* dout, const float* oraw, float* gs,
                       const double* stats, double* bstats, float* bcoef, unsigned* bcnt, cudaStream_t st);
 int launch_bwd_proj(const Dims& m, const MtAxialParams& p, const MtAxialGrads& gr, const float* x, const float* bcoef,
@@ -415,7 +419,14 @@ int axial_backward_launch(const Dims& m, const MtAxialParams& p, const float* x,
   const bool p2 = (m.L & (m.L - 1)) == 0;
   const int segw = p2 ? (m.L < 32 ? m.L : 32) : 1;
   (void)pow2_le;
-  if (mask & 2) {  // T = sum dZ*S_t is needed in eval mode too (bn_similarity.weight and the gate gradients)
+  const bool v1 = (m.dbg & 2) != 0;
+  int r2 = 0;
+  if ((mask & 2) && !v1) {
+    r2 = launch_bwd2<0>(m, p, gr, stats, bstats, coef, bcoef, bcnt, yraw, oraw, lse, gs, dyh, st);
+    if (r2 < 0) return -1;
+    nl += r2;
+  }
+  if ((mask & 2) && r2 == 0) {  // T = sum dZ*S_t is needed in eval mode too (bn_similarity.weight and the gate gradients)
     const size_t smem = bwd_smem_floats(m, spb, 24) * sizeof(float);
     if (smem > 227 * 1024) return -2;
 #define CALL_BS(DD, PP)                                                                               \
@@ -425,7 +436,14 @@ int axial_backward_launch(const Dims& m, const MtAxialParams& p, const float* x,
 #undef CALL_BS
     ++nl;
   }
-  if (mask & 4) {
+  r2 = 0;
+  if ((mask & 4) && !v1) {
+    if (m.pos && !gr.drelative) return -3;
+    r2 = launch_bwd2<1>(m, p, gr, stats, bstats, coef, bcoef, bcnt, yraw, oraw, lse, gs, dyh, st);
+    if (r2 < 0) return -1;
+    nl += r2;
+  }
+  if ((mask & 4) && r2 == 0) {
     const int nrel = m.pos ? 2 * m.gp * (2 * m.L - 1) : 0;
     const size_t smem = bwd_smem_floats(m, spb, 4 * m.C + nrel) * sizeof(float);
     if (smem > 227 * 1024) return -2;
