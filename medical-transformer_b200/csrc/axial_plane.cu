@@ -101,26 +101,41 @@ __device__ __forceinline__ void gather_reduce(const Dims& m, const MtAxialParams
   if (last_cta_done(bcnt + 0, gridDim.x * gridDim.y * gridDim.z)) fin_bwd_out(m, p, stats, bstats, bcoef);
 }
 
-// grid (ceil(H*W / blockDim), N*C): one full-resolution position per thread
+// grid (splits, C, groups): a CTA walks a chunk of the (group, channel) slab of npg*H*W full-resolution
+// positions, 4 independent loads in flight per thread; one ticket per CTA (not per plane).
 __global__ void __launch_bounds__(256)
 k_bwd_gather_direct(Dims m, MtAxialParams p, const float* __restrict__ dout, const float* __restrict__ oraw,
                     float* __restrict__ gs, const double* __restrict__ stats, double* __restrict__ bstats,
-                    float* __restrict__ bcoef, unsigned* __restrict__ bcnt) {
-  const int plane = blockIdx.y, n = plane / m.C, c = plane - n * m.C;
-  const int NO = m.no, L = m.L, st_ = m.stride, Ho = m.H / st_, Wo = m.W / st_;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+                    float* __restrict__ bcoef, unsigned* __restrict__ bcnt, int chunk) {
+  const int c = blockIdx.y, grp = blockIdx.z, npg = m.N / m.ngroups;
+  const int NO = m.no, L = m.L, st_ = m.stride, Ho = m.H / st_, Wo = m.W / st_, HW = m.H * m.W;
+  const int cnt = npg * HW, e0 = blockIdx.x * chunk, e1 = e0 + chunk < cnt ? e0 + chunk : cnt;
+  const float inv = 1.f / (float)(st_ * st_);
   float s1 = 0.f, s2a = 0.f, s2b = 0.f;
-  if (idx < m.H * m.W) {
-    const int h = idx / m.W, w = idx - h * m.W;
-    const float g = __ldg(dout + ((size_t)plane * Ho + h / st_) * Wo + w / st_) * (1.f / (float)(st_ * st_));
-    const int b = m.axis == 0 ? n * m.W + w : n * m.H + h;
-    const int l = m.axis == 0 ? h : w;
-    gs[((size_t)b * m.C + c) * L + l] = g;
-    const float* o = oraw + ((size_t)b * NO * m.C + c * NO) * L + l;
-    s1 = g; s2a = g * __ldg(o);
-    if (NO == 2) s2b = g * __ldg(o + L);
+  for (int base = e0; base < e1; base += 4 * blockDim.x) {
+    float g[4], oa[4], ob[4];
+    size_t go[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = base + u * blockDim.x + threadIdx.x;
+      g[u] = 0.f; oa[u] = 0.f; ob[u] = 0.f; go[u] = 0;
+      if (e < e1) {
+        const int nl = e / HW, r = e - nl * HW, h = r / m.W, w = r - h * m.W, n = grp * npg + nl;
+        g[u] = __ldg(dout + ((size_t)(n * m.C + c) * Ho + h / st_) * Wo + w / st_) * inv;
+        const int b = m.axis == 0 ? n * m.W + w : n * m.H + h, l = m.axis == 0 ? h : w;
+        go[u] = ((size_t)b * m.C + c) * L + l;
+        const float* o = oraw + ((size_t)b * NO * m.C + c * NO) * L + l;
+        oa[u] = __ldg(o);
+        if (NO == 2) ob[u] = __ldg(o + L);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = base + u * blockDim.x + threadIdx.x;
+      if (e < e1) { gs[go[u]] = g[u]; s1 += g[u]; s2a = fmaf(g[u], oa[u], s2a); s2b = fmaf(g[u], ob[u], s2b); }
+    }
   }
-  gather_reduce(m, p, s1, s2a, s2b, c, n / (m.N / m.ngroups), stats, bstats, bcoef, bcnt, blockIdx.x + blockIdx.y);
+  gather_reduce(m, p, s1, s2a, s2b, c, grp, stats, bstats, bcoef, bcnt, blockIdx.x + blockIdx.y);
 }
 
 // axis 0, stride 1: 32x32 tile transpose.  grid (ceil(W/32), ceil(H/32), N*C)
@@ -157,7 +172,7 @@ k_bwd_gather_t(Dims m, MtAxialParams p, const float* __restrict__ dout, const fl
 
 // ---------------------------------------------------------------------------- host launchers
 int launch_out(const Dims& m, const float* coef, const float* oraw, float* out, cudaStream_t st) {
-  if (m.axis == 0 && m.stride == 1) {
+  if (m.axis == 0 && m.stride == 1 && m.H >= 32 && m.W >= 32) {
     dim3 grid((m.W + 31) / 32, (m.H + 31) / 32, m.N * m.C);
     k_out_t<<<grid, 256, 0, st>>>(m, coef, oraw, out);
   } else {
@@ -169,14 +184,15 @@ int launch_out(const Dims& m, const float* coef, const float* oraw, float* out, 
 
 int launch_bwd_gather(const Dims& m, const MtAxialParams& p, const float* dout, const float* oraw, float* gs,
                       const double* stats, double* bstats, float* bcoef, unsigned* bcnt, cudaStream_t st) {
-  if (m.axis == 0 && m.stride == 1) {
+  if (m.axis == 0 && m.stride == 1 && m.H >= 32 && m.W >= 32) {
     dim3 grid((m.W + 31) / 32, (m.H + 31) / 32, m.N * m.C);
     k_bwd_gather_t<<<grid, 256, 0, st>>>(m, p, dout, oraw, gs, stats, bstats, bcoef, bcnt);
-  } else {
-    const int hw = m.H * m.W;
-    int bs = hw >= 256 ? 256 : ((hw + 31) / 32) * 32;
-    dim3 grid((hw + bs - 1) / bs, m.N * m.C);
-    k_bwd_gather_direct<<<grid, bs, 0, st>>>(m, p, dout, oraw, gs, stats, bstats, bcoef, bcnt);
+  } else {       // small planes (everything is L2 resident; full 32x32 tiles would be mostly empty) and width-axis ops
+    const int cnt = (m.N / m.ngroups) * m.H * m.W;
+    const int chunk = cnt > 4096 ? 4096 : ((cnt + 1023) / 1024) * 1024;
+    const int bs = cnt >= 1024 ? 256 : (cnt >= 256 ? 64 : 32);
+    dim3 grid((cnt + chunk - 1) / chunk, m.C, m.ngroups);
+    k_bwd_gather_direct<<<grid, bs, 0, st>>>(m, p, dout, oraw, gs, stats, bstats, bcoef, bcnt, chunk);
   }
   return 1;
 }

@@ -9,10 +9,12 @@
 
 #define MT_G 8              // heads: fixed by the reference (axialnet.py:400)
 #define MT_LOG2E 1.4426950408889634f
-#define MT_NREP 8           // replicated fp64 accumulator slots (CTA picks blockIdx & 7): cuts same-address atomic serialisation
+#define MT_NREP 8           // max replicated fp64 accumulator slots (CTA picks blockIdx % nrep): cuts same-address atomic
+                            // serialisation; used only when there are few statistic groups (m.nrep)
 
 struct Dims {
   int N, C, H, W, axis, stride, variant, training, ngroups;
+  int nrep;                // accumulator replicas in use: 8 when ngroups < 4, else 1 (groups already spread the atomics)
   int dbg;                 // MT_DEBUG_FLAGS env (timing experiments only): bit0 = skip global statistic atomics
   int L, other, B, Bg, gp, d, nt, no, LP, pos;
   float eps, momentum;
@@ -42,6 +44,7 @@ static inline bool make_dims(const MtAxialDesc* d, Dims& m) {
   if (m.variant < 0 || m.variant > 2) return false;
   if (m.N % m.ngroups) return false;
   if (m.C % (2 * MT_G)) return false;
+  m.nrep = m.ngroups < 4 ? MT_NREP : 1;
   m.L = m.axis == 0 ? m.H : m.W;
   m.other = m.axis == 0 ? m.W : m.H;
   m.B = m.N * m.other;
@@ -65,7 +68,7 @@ static inline bool make_dims(const MtAxialDesc* d, Dims& m) {
   m.cf_q = 0; m.cf_s = 4 * C; m.cf_o = m.cf_s + 2 * m.nt * MT_G; m.ncoef_f = m.cf_o + 2 * m.no * C;
   m.cb_o = 0; m.cb_s = 3 * m.no * C; m.cb_q = m.cb_s + 3 * m.nt * MT_G; m.ncoef_b = m.cb_q + 6 * C;
   size_t off = 0;
-  m.sv_stats = off; off += sizeof(double) * (size_t)MT_NREP * m.ngroups * m.nstat_f;
+  m.sv_stats = off; off += sizeof(double) * (size_t)m.nrep * m.ngroups * m.nstat_f;
   m.sv_cnt = off;   off = mt_align(off + 64);          // CTA-done tickets, zeroed together with the accumulators
   m.sv_zero_bytes = off;
   m.sv_coef = off;  off = mt_align(off + sizeof(float) * (size_t)m.ngroups * m.ncoef_f);
@@ -74,7 +77,7 @@ static inline bool make_dims(const MtAxialDesc* d, Dims& m) {
   m.sv_lse = off;   off = mt_align(off + sizeof(float) * (size_t)m.B * MT_G * m.L);
   m.sv_bytes = off;
   off = 0;
-  m.ws_bstats = off; off += sizeof(double) * (size_t)MT_NREP * m.ngroups * m.nstat_b;
+  m.ws_bstats = off; off += sizeof(double) * (size_t)m.nrep * m.ngroups * m.nstat_b;
   m.ws_cnt = off;    off = mt_align(off + 64);
   m.ws_zero_bytes = off;
   m.ws_coef = off;   off = mt_align(off + sizeof(float) * (size_t)m.ngroups * m.ncoef_b);
@@ -168,12 +171,15 @@ __device__ __forceinline__ BnBwdCoef bn_bwd_coef(int training, double sum, doubl
 
 // replicated accumulators: layout [MT_NREP][ngroups][nstat]
 __device__ __forceinline__ double* stat_slot(const Dims& m, double* base, int grp, int nstat, int cta) {
-  return base + ((size_t)(cta & (MT_NREP - 1)) * m.ngroups + grp) * nstat;
+  return base + ((size_t)(cta & (m.nrep - 1)) * m.ngroups + grp) * nstat;
 }
 __device__ __forceinline__ double stat_get(const Dims& m, const double* base, int grp, int nstat, int off) {
-  double s = 0.0;
+  if (m.nrep == 1) return __ldcg(base + (size_t)grp * nstat + off);
+  double v[MT_NREP], s = 0.0;
 #pragma unroll
-  for (int r = 0; r < MT_NREP; ++r) s += __ldcg(base + ((size_t)r * m.ngroups + grp) * nstat + off);
+  for (int r = 0; r < MT_NREP; ++r) v[r] = __ldcg(base + ((size_t)r * m.ngroups + grp) * nstat + off);   // 8 loads in flight
+#pragma unroll
+  for (int r = 0; r < MT_NREP; ++r) s += v[r];
   return s;
 }
 
