@@ -43,7 +43,9 @@ k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stat
   extern __shared__ __align__(16) float sm[];
   const int C = m.C, L = m.L, LP = m.LP, NOC = NO * C, RP = rel_pitch(L), LB = L / RT;
   const int b0 = blockIdx.x * SPB, grp = b0 / m.Bg;
-  const int phase = MODE == 0 ? 0 : (int)blockIdx.y;            // MODE 1: 0 rows, 1 columns, 2 diagonals
+  // MODE 1: y = 0 rows, 1 columns, 2.. diagonals (the scalar diagonal walk is split over NDS CTAs)
+  const int phase = MODE == 0 ? 0 : ((int)blockIdx.y < 2 ? (int)blockIdx.y : 2);
+  const int dsplit = (int)blockIdx.y - 2, nds = (int)gridDim.y - 2;
   const int nrel = POS ? 2 * GP * (2 * L - 1) : 0;
   const int nred = MODE == 0 ? 24 : 4 * C + nrel;
   Bwd2Smem s = carve2(m, sm, SPB, nred);
@@ -320,7 +322,8 @@ k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stat
   // ------------------------------------------------------------ diagonals (d relative), scalar walk
   if (MODE == 1 && POS && phase == 2) {
     const int RL = 2 * L - 1, nd = SPB * MT_G * RL;
-    for (int item = threadIdx.x; item < nd; item += blockDim.x) {
+    const int per = (nd + nds - 1) / nds, i0 = dsplit * per, i1 = i0 + per < nd ? i0 + per : nd;
+    for (int item = i0 + threadIdx.x; item < i1; item += blockDim.x) {
       const int mm = item % RL, g = (item / RL) % MT_G, ss = item / (RL * MT_G);
       const float* Yb = s.Yn + ((size_t)ss * 2 * C + g * 4 * D) * LP;
       const float* dOb = s.dOs + ((size_t)ss * NOC + g * GP * NO) * LP;
@@ -400,7 +403,7 @@ static int launch_b(const Dims& m, const MtAxialParams& p, const MtAxialGrads& g
   if (smem > 32 * 1024 &&
       cudaFuncSetAttribute(k_bwd2<D, POS, RT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return -1;
-  const dim3 grid(m.B / spb, MODE == 0 ? 1 : (POS ? 3 : 2));
+  const dim3 grid(m.B / spb, MODE == 0 ? 1 : (POS ? 2 + 4 : 2));      // rows, columns, 4 x diagonals
   k_bwd2<D, POS, RT, MODE><<<grid, 128, smem, st>>>(m, p, gr, stats, bstats, coef, bcoef, bcnt, yraw, oraw, lse, gs, dyh,
                                                     spb, segw);
   return 1;

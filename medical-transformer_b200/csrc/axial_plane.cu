@@ -189,8 +189,11 @@ int launch_bwd_gather(const Dims& m, const MtAxialParams& p, const float* dout, 
     k_bwd_gather_t<<<grid, 256, 0, st>>>(m, p, dout, oraw, gs, stats, bstats, bcoef, bcnt);
   } else {       // small planes (everything is L2 resident; full 32x32 tiles would be mostly empty) and width-axis ops
     const int cnt = (m.N / m.ngroups) * m.H * m.W;
-    const int chunk = cnt > 4096 ? 4096 : ((cnt + 1023) / 1024) * 1024;
-    const int bs = cnt >= 1024 ? 256 : (cnt >= 256 ? 64 : 32);
+    // ~1024 CTAs in total: enough to fill the GPU, few enough that the CTA-done tickets (one same-address
+    // atomic each; 8192 of them cost > 100 us on the batched LoGo branch) stay cheap
+    long want = ((long)cnt * m.C * m.ngroups / 1024 + 255) / 256 * 256;
+    const int chunk = want < 256 ? 256 : (want > 4096 ? 4096 : (int)want);
+    int bs = chunk / 4; if (bs > 256) bs = 256; if (bs > cnt) bs = ((cnt + 31) / 32) * 32; if (bs < 32) bs = 32;
     dim3 grid((cnt + chunk - 1) / chunk, m.C, m.ngroups);
     k_bwd_gather_direct<<<grid, bs, 0, st>>>(m, p, dout, oraw, gs, stats, bstats, bcoef, bcnt, chunk);
   }

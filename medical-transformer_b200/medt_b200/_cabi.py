@@ -45,7 +45,8 @@ EXPORTS = ["mt_version", "mt_last_error", "mt_last_launch_count", "mt_axial_save
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libmedt_b200.so")
+    # MEDT_LIB_PATH: developer override used for same-box A/B runs of two builds
+    return os.environ.get("MEDT_LIB_PATH") or os.path.join(_HERE, "libmedt_b200.so")
 
 
 def load_library():
