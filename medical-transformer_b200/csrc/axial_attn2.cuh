@@ -51,6 +51,40 @@ struct WinB {
   __device__ __forceinline__ float get(int r, int w) const { const int d = w - r; return d >= 0 ? hi[d] : lo[RT + d]; }
 };
 
+// ---------------------------------------------------------------------------------------------
+// TMA (bulk async copy) staging of the q/k/v strips.  A CTA's strips are one contiguous block of
+// SPB*2C*L floats in y_raw (strip-major layout) and, when LP == L, also in shared memory, so ONE
+// cp.async.bulk (SASS: UBLKCP) issued by thread 0 at kernel start brings them in while the other
+// threads load coefficient tables and Toeplitz tables; completion is signalled on an mbarrier.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_strips_issue(uint64_t* bar, float* dst, const float* src, uint32_t bytes) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(1) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_strips_wait(uint64_t* bar) {
+  uint32_t ok = 0, spins = 0;
+  while (!ok) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(0) : "memory");
+    if (!ok && ++spins > (1u << 22)) __trap();          // never hang the GPU on a lost copy
+  }
+}
+// in-place BN affine on the staged block: row r uses (a, b)[r % ncoef]
+__device__ __forceinline__ void affine_rows_inplace(float* Yn, int nrows, int L, const float* a, const float* b, int ncoef) {
+  const int L4 = L >> 2, total4 = nrows * L4;
+  float4* y4 = reinterpret_cast<float4*>(Yn);
+  for (int i4 = threadIdx.x; i4 < total4; i4 += blockDim.x) {
+    const int rc = (i4 / L4) % ncoef;
+    const float ka = a[rc], kb = b[rc];
+    float4 v = y4[i4];
+    v.x = fmaf(ka, v.x, kb); v.y = fmaf(ka, v.y, kb); v.z = fmaf(ka, v.z, kb); v.w = fmaf(ka, v.w, kb);
+    y4[i4] = v;
+  }
+}
+
 // shared-memory pitch of one Toeplitz table row in the v2 layout (plain copy; the shifted copy
 // follows at +RP): 2L entries used, padded so the last window pre-load stays in bounds
 __host__ __device__ __forceinline__ int rel_pitch(int L) { return 2 * L + 8; }

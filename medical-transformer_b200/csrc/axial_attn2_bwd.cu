@@ -50,6 +50,10 @@ k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stat
   const int nred = MODE == 0 ? 24 : 4 * C + nrel;
   Bwd2Smem s = carve2(m, sm, SPB, nred);
   float* dRs = s.red + 4 * C;
+  __shared__ __align__(8) uint64_t tma_bar;
+  const bool use_tma = (LP == L);
+  if (use_tma && threadIdx.x == 0)
+    tma_strips_issue(&tma_bar, s.Yn, yraw + (size_t)b0 * 2 * C * L, (uint32_t)(SPB * 2 * C * L * sizeof(float)));
   for (int k = threadIdx.x; k < nred; k += blockDim.x) s.red[k] = 0.f;
   // ---- staging (coefficient tables -> strips, dO, lse -> D), batched loads
   {
@@ -68,7 +72,8 @@ k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stat
     if (POS) load_rel2(m, p.relative, s.Rp, s.Rs);
   }
   __syncthreads();
-  stage_rows(yraw + (size_t)b0 * 2 * C * L, SPB * 2 * C, L, LP, s.ca, s.cb, 2 * C, s.Yn);
+  if (use_tma) { tma_strips_wait(&tma_bar); affine_rows_inplace(s.Yn, SPB * 2 * C, L, s.ca, s.cb, 2 * C); }
+  else stage_rows(yraw + (size_t)b0 * 2 * C * L, SPB * 2 * C, L, LP, s.ca, s.cb, 2 * C, s.Yn);
   {
     const int per4 = NOC * L / 4, L4 = L / 4;
     const float4* so = reinterpret_cast<const float4*>(oraw + (size_t)b0 * NOC * L);

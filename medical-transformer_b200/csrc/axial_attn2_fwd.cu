@@ -22,6 +22,10 @@ k_attn2(Dims m, MtAxialParams p, const float* __restrict__ yraw, double* __restr
   float* Rp = Yn + (size_t)SPB * 2 * C * LP;        // plain tables
   float* Rs = Rp + 2 * GP * RP;                     // shifted tables
   const int b0 = blockIdx.x * SPB, grp = b0 / m.Bg;
+  __shared__ __align__(8) uint64_t tma_bar;
+  const bool use_tma = (LP == L) && ((L & 3) == 0);
+  if (use_tma && threadIdx.x == 0)
+    tma_strips_issue(&tma_bar, Yn, yraw + (size_t)b0 * 2 * C * L, (uint32_t)(SPB * 2 * C * L * sizeof(float)));
   {
     const float* tb = coef + (size_t)grp * m.ncoef_f + m.cf_q;
     for (int ch = threadIdx.x; ch < 2 * C; ch += blockDim.x) { ca[ch] = tb[2 * ch]; cb[ch] = tb[2 * ch + 1]; }
@@ -30,7 +34,8 @@ k_attn2(Dims m, MtAxialParams p, const float* __restrict__ yraw, double* __restr
   for (int k = threadIdx.x; k < nred; k += blockDim.x) red[k] = 0.f;
   if (POS) load_rel2(m, p.relative, Rp, Rs);
   __syncthreads();
-  stage_rows(yraw + (size_t)b0 * 2 * C * L, SPB * 2 * C, L, LP, ca, cb, 2 * C, Yn);
+  if (use_tma) { tma_strips_wait(&tma_bar); affine_rows_inplace(Yn, SPB * 2 * C, L, ca, cb, 2 * C); }
+  else stage_rows(yraw + (size_t)b0 * 2 * C * L, SPB * 2 * C, L, LP, ca, cb, 2 * C, Yn);
   __syncthreads();
 
   const int nitems = SPB * MT_G * LB;

@@ -227,8 +227,12 @@ class medt_net(_ShellBase):
     4x4 grid of 32-px patches, merged before the head."""
 
     def __init__(self, block, block_2, layers, num_classes=2, zero_init_residual=True, groups=8, width_per_group=64,
-                 replace_stride_with_dilation=None, norm_layer=None, s=0.125, img_size=128, imgchan=3):
+                 replace_stride_with_dilation=None, norm_layer=None, s=0.125, img_size=128, imgchan=3, patch_size=None):
         super().__init__()
+        # patch_size=None keeps the reference's hard-coded 32-px patches (bug-compatible: at img_size != 128
+        # only the top-left 128x128 gets local features and `logo` cannot run); patch_size=img_size//4 is the
+        # generalisation SURVEY 8(f)-1 asks for (identical to the reference at 128 px).
+        self._patch = PATCH if patch_size is None else int(patch_size)
         self._norm_layer = norm_layer = nn.BatchNorm2d if norm_layer is None else norm_layer
         self.inplanes = int(64 * s)
         self.dilation = 1
@@ -275,6 +279,7 @@ class medt_net(_ShellBase):
 
     def _local_branch(self, xin):
         n = xin.shape[0]
+        PATCH = self._patch
         side = PATCH * GRID
         # (N,3,128,128) -> (16N,3,32,32), patch-major in the reference's (i, j) loop order
         xp = xin[:, :, :side, :side].reshape(n, -1, GRID, PATCH, GRID, PATCH).permute(2, 4, 0, 1, 3, 5)
@@ -300,7 +305,7 @@ class medt_net(_ShellBase):
         x2 = self.layer2(x1)
         x = _up_relu(self.decoder4, x2, x1)
         x = _up_relu(self.decoder5, x)
-        side = PATCH * GRID
+        side = self._patch * GRID
         x_loc = x.clone()                       # outside the 128x128 patch grid x_loc stays == x (:658,:700)
         x_loc[:, :, :side, :side] = self._local_branch(xin)
         x = F.relu(self.decoderf(x + x_loc))

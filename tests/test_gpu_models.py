@@ -124,3 +124,49 @@ def test_train_step_graph_equals_eager():
     # identical kernels; atomics order differs run to run and training amplifies it step by step
     assert np.allclose(losses[0][:2], losses[1][:2], rtol=1e-3) and np.allclose(losses[0], losses[1], rtol=3e-2), losses
     assert losses[0][2] < losses[0][0]          # it learns on a fixed batch
+
+
+def test_logo_patch_generalisation_256px_matches_oracle():
+    """SURVEY 8(f)-1: patch = img_size//4 makes `logo` runnable at 256 px (the reference crashes there);
+    checked against the oracle's patch loop with the constant substituted (eval mode + train mode)."""
+    import lib
+    from oracle import torch_port
+    torch.manual_seed(5)
+    m = lib.models.axialnet.logo(img_size=256, imgchan=3, patch_size=64)
+    x = torch.rand(1, 3, 256, 256)
+    ref_m = lib.models.axialnet.logo(img_size=256, imgchan=3, patch_size=64)
+    ref_m.load_state_dict(m.state_dict())
+    for mode in ("eval", "train"):
+        m.train(mode == "train"); ref_m.train(mode == "train")
+        with torch.no_grad():
+            ref = torch_port.forward(ref_m.double(), x.double(), patch=64).float()
+            got = m.cuda()(x.cuda()).cpu()
+        rel = ((got - ref).norm() / ref.norm()).item()
+        assert rel < (5e-3 if mode == "train" else 1e-4), (mode, rel)
+
+
+def test_long_sequence_L256_matches_oracle():
+    """BASELINE config 5 sequence length (L = 256 at 512 px): one gated op, strips of 256."""
+    from oracle import axial_np
+    from test_gpu_axial import build_module
+    rs = np.random.RandomState(7)
+    C, L, Wd = 16, 256, 8
+    name = "long.gated.256"
+    p = {"w_qkv": fill.tensor_for(name + ".qkv_transform.weight", (2 * C, C))}
+    for bn, short, n in (("bn_qkv", "bn_qkv", 2 * C), ("bn_similarity", "bn_sim", 24), ("bn_output", "bn_out", 2 * C)):
+        for leaf, suf in (("weight", "_w"), ("bias", "_b"), ("running_mean", "_rm"), ("running_var", "_rv")):
+            p[short + suf] = fill.tensor_for(f"{name}.{bn}.{leaf}", (n,))
+    p["relative"] = fill.tensor_for(name + ".relative", (4, 2 * L - 1))
+    p["gates"] = (0.1, 0.1, 1.0, 0.1)
+    x = rs.standard_normal((1, C, L, Wd))
+    cfg = dict(C=C, N=1, H=L, W=Wd, axis=0, stride=1, ngroups=1, variant="gated", L=L)
+    out_ref, cache, _ = axial_np.axial_forward(x, p, 0, 1, "gated", training=True)
+    dout = rs.standard_normal(out_ref.shape)
+    gref = axial_np.axial_backward(dout, cache)
+    mod = build_module(cfg, p, name).train()
+    xt = torch.tensor(x, dtype=torch.float32, device="cuda", requires_grad=True)
+    out = mod(xt)
+    out.backward(torch.tensor(dout, dtype=torch.float32, device="cuda"))
+    assert rel_err(out.detach().cpu().numpy(), out_ref) < 1e-4
+    assert rel_err(xt.grad.cpu().numpy(), gref["dx"]) < 2e-3
+    assert rel_err(mod.relative.grad.cpu().numpy(), gref["drelative"]) < 2e-3
