@@ -11,6 +11,7 @@
  *                         hand-written backward; train.py:160 calls loss.backward())
  *   mt_bn_act_*        <- BatchNorm2d(+ReLU)(+residual) glue of the blocks / stems / LoGo loop
  *   mt_up2x_relu_add_* <- relu(bilinear x2) + skip of the decoders
+ *   mt_conv1x1_*       <- the bias-free 1x1 convolutions of the blocks
  *
  * Conventions
  *   - plain C, no torch types; all pointers are DEVICE pointers unless named host_*;
@@ -130,6 +131,14 @@ int mt_bn_act_forward(int N, int C, int HW, int groups, int training, int relu, 
 int mt_bn_act_backward(int N, int C, int HW, int groups, int training, int relu, const float* x, const float* y,
                        const float* dy, const float* gamma, const float* save_mean, const float* save_invstd,
                        float* dx, float* dresidual, float* dgamma, float* dbeta, void* stream);
+
+/* Bias-free 1x1 convolution (conv_down / conv_up / downsample of the blocks: `conv1x1`, axialnet.py:14-16,
+ * :272-276, :450-453) as a tiled fp32 SGEMM.  x: (N,Ci,H,W), w: (Co,Ci), y / dy: (N,Co,Ho,Wo) with
+ * Ho = (H-1)/stride+1.  backward overwrites dx (N,Ci,H,W) and dw (Co,Ci); either may be NULL. */
+int mt_conv1x1_forward(int N, int Ci, int Co, int H, int W, int stride, const float* x, const float* w, float* y,
+                       void* stream);
+int mt_conv1x1_backward(int N, int Ci, int Co, int H, int W, int stride, const float* x, const float* w,
+                        const float* dy, float* dx, float* dw, void* stream);
 
 /* Profiling hooks (bench.py roofline, ncu): launch only the stages selected by `stage_mask`
  * of a forward (bit 0 k_proj, 1 k_sim_stats, 2 k_attn, 3 k_out) or backward (bit 0

@@ -158,7 +158,12 @@ k_bn_act_fwd(BnActArgs a, const float* __restrict__ x, const float* __restrict__
     invstd = rsqrt_nr(var + a.eps);
     if (threadIdx.x == 0) {
       save_mean[g * a.C + c] = mean; save_invstd[g * a.C + c] = invstd;
-      save_mean[(a.G + g) * a.C + c] = var;                 // biased variance, for the EMA below
+      save_mean[(a.G + g) * a.C + c] = var;                 // biased variance, for the grouped EMA kernel
+      if (a.G == 1) {                                       // single statistic group: EMA right here, no extra launch
+        const float unb = cnt > 1 ? (float)cnt / (float)(cnt - 1) : 1.f;
+        rm[c] = (1.f - a.momentum) * rm[c] + a.momentum * mean;
+        rv[c] = (1.f - a.momentum) * rv[c] + a.momentum * var * unb;
+      }
     }
   } else {
     mean = rm[c]; invstd = rsqrt_nr(rv[c] + a.eps);
@@ -349,7 +354,8 @@ int mt_bn_act_forward(int N, int C, int HW, int groups, int training, int relu, 
   else
     k_bn_act_fwd<false><<<dim3(C, groups), bs, 0, (cudaStream_t)stream>>>(a, x, residual, gamma, beta, running_mean,
                                                                             running_var, y, save_mean, save_invstd);
-  if (training) k_bn_ema<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a, save_mean, running_mean, running_var);
+  if (training && groups > 1)   // sequential EMA over the statistic groups (one BN call per patch in the reference)
+    k_bn_ema<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a, save_mean, running_mean, running_var);
   g_last_cuda = cudaGetLastError();
   return g_last_cuda == cudaSuccess ? MT_OK : mt_fail_msg(MT_ERR_CUDA, "mt_bn_act_forward: launch failed");
 }

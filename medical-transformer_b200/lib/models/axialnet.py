@@ -20,7 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from medt_b200.axial_op import axial_attention
-from medt_b200.shell_ops import bn_act, up2x_relu_add
+from medt_b200.shell_ops import bn_act, conv1x1 as conv1x1_op, up2x_relu_add
 
 from .utils import qkv_transform
 
@@ -116,11 +116,11 @@ class _AxialBlockBase(nn.Module):
 
     def forward(self, x):
         g = self._stat_groups
-        out = bn_act(self.conv_down(x), self.bn1, g, relu=True)
+        out = bn_act(conv1x1_op(x, self.conv_down), self.bn1, g, relu=True)
         out = self.width_block(self.hight_block(out))
         if self.downsample is not None:
-            x = bn_act(self.downsample[0](x), self.downsample[1], g, relu=False)
-        return bn_act(self.conv_up(F.relu(out)), self.bn2, g, relu=True, residual=x)
+            x = bn_act(conv1x1_op(x, self.downsample[0]), self.downsample[1], g, relu=False)
+        return bn_act(conv1x1_op(F.relu(out), self.conv_up), self.bn2, g, relu=True, residual=x)
 
 
 class AxialBlock(_AxialBlockBase):

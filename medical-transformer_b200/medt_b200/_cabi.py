@@ -41,7 +41,8 @@ class MtAxialGrads(C.Structure):
 EXPORTS = ["mt_version", "mt_last_error", "mt_last_launch_count", "mt_axial_saved_bytes",
            "mt_axial_bwd_workspace_bytes", "mt_axial_forward", "mt_axial_backward",
            "mt_axial_forward_stages", "mt_axial_backward_stages",
-           "mt_up2x_relu_add_forward", "mt_up2x_relu_add_backward", "mt_bn_act_forward", "mt_bn_act_backward"]
+           "mt_up2x_relu_add_forward", "mt_up2x_relu_add_backward", "mt_bn_act_forward", "mt_bn_act_backward",
+           "mt_conv1x1_forward", "mt_conv1x1_backward"]
 
 
 def lib_path() -> str:
@@ -88,6 +89,10 @@ def load_library():
         lib.mt_bn_act_forward.argtypes = [I, I, I, I, I, I, F_, F_, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP]
         lib.mt_bn_act_backward.restype = C.c_int
         lib.mt_bn_act_backward.argtypes = [I, I, I, I, I, I, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP]
+        lib.mt_conv1x1_forward.restype = C.c_int
+        lib.mt_conv1x1_forward.argtypes = [I, I, I, I, I, I, VP, VP, VP, VP]
+        lib.mt_conv1x1_backward.restype = C.c_int
+        lib.mt_conv1x1_backward.argtypes = [I, I, I, I, I, I, VP, VP, VP, VP, VP, VP]
         _LIB = lib
         return lib
 

@@ -84,7 +84,7 @@ class BnAct(torch.autograd.Function):
                                        _p(weight), _p(bias), _p(rm), _p(rv), _p(y), _p(save_mean), _p(save_invstd),
                                        _stream(x.device))
         _cabi.check(rc, "mt_bn_act_forward")
-        _cabi.LAUNCHES["kernels"] += 2 if training else 1
+        _cabi.LAUNCHES["kernels"] += 2 if (training and groups > 1) else 1
         ctx.cfg = cfg
         ctx.has_res = residual is not None
         ctx.save_for_backward(x, y, weight, save_mean, save_invstd)
@@ -124,3 +124,45 @@ def bn_act(x, bn, groups: int = 1, relu: bool = True, residual=None):
             with torch.no_grad():
                 bn.num_batches_tracked += g
     return y
+
+
+class Conv1x1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, stride):
+        _need_cuda(x, "conv1x1")
+        lib = _cabi.load_library()
+        x = x.contiguous()
+        n, ci, h, w = x.shape
+        co = weight.shape[0]
+        ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+        y = torch.empty((n, co, ho, wo), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.mt_conv1x1_forward(n, ci, co, h, w, stride, _p(x), _p(weight), _p(y), _stream(x.device))
+        _cabi.check(rc, "mt_conv1x1_forward")
+        _cabi.LAUNCHES["kernels"] += 1
+        ctx.save_for_backward(x, weight)
+        ctx.stride = stride
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        lib = _cabi.load_library()
+        dy = dy.contiguous()
+        n, ci, h, w = x.shape
+        co = weight.shape[0]
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(weight) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(x.device):
+            rc = lib.mt_conv1x1_backward(n, ci, co, h, w, ctx.stride, _p(x), _p(weight), _p(dy), _p(dx), _p(dw),
+                                         _stream(x.device))
+        _cabi.check(rc, "mt_conv1x1_backward")
+        _cabi.LAUNCHES["kernels"] += (1 if dx is not None else 0) + (1 if dw is not None else 0)
+        return dx, dw, None
+
+
+def conv1x1(x, conv):
+    """`conv` is the module's own bias-free nn.Conv2d(kernel_size=1) (weight (Co,Ci,1,1) used in place)."""
+    if conv.bias is not None or conv.kernel_size != (1, 1):
+        return conv(x)
+    return Conv1x1.apply(x, conv.weight, int(conv.stride[0]))

@@ -57,6 +57,26 @@ def test_bn_act_matches_torch(n, c, h, w, groups, relu, with_res, training):
         assert (u - v).norm() <= 2e-4 * max(v.norm().item(), 1e-3), (u - v).norm() / v.norm()
 
 
+@pytest.mark.parametrize("n,ci,co,h,w,stride", [(4, 8, 16, 64, 64, 1), (4, 32, 64, 64, 64, 2), (2, 128, 256, 16, 16, 2),
+                                                 (64, 64, 128, 4, 4, 1), (3, 5, 7, 6, 10, 1), (2, 16, 32, 5, 7, 2)])
+def test_conv1x1_matches_torch(n, ci, co, h, w, stride):
+    from medt_b200.shell_ops import conv1x1
+    torch.manual_seed(3)
+    conv = torch.nn.Conv2d(ci, co, kernel_size=1, stride=stride, bias=False).cuda()
+    x = torch.randn(n, ci, h, w, device="cuda", requires_grad=True)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    ref = conv(x)
+    got = conv1x1(x, conv)
+    assert got.shape == ref.shape and torch.allclose(got, ref, atol=1e-5, rtol=1e-5)
+    d = torch.randn_like(ref)
+    gr = torch.autograd.grad(ref, (x, conv.weight), d)
+    gg = torch.autograd.grad(got, (x, conv.weight), d)
+    torch.backends.cudnn.allow_tf32 = tf32
+    for u, v in zip(gg, gr):
+        assert (u - v).norm() <= 1e-4 * max(v.norm().item(), 1e-3)
+
+
 def test_shell_ops_refuse_cpu():
     from medt_b200.shell_ops import up2x_relu_add
     with pytest.raises(RuntimeError, match="no CPU fallback"):
