@@ -9,6 +9,46 @@
 #include "axial_attn2.cuh"
 extern thread_local cudaError_t g_last_cuda;
 
+// Mirror accumulators of WinA / WinB: a pair (r, w) adds its contribution to the slot it read the table
+// value from; after each step one RT-block is complete for this thread and is flushed to the CTA's
+// shared-memory d relative accumulator (plain index m).  This replaces the separate diagonal walk.
+template <int RT>
+struct AccA {            // pairs index  own - walk + L - 1 ; slot layout of WinA (hi = block K, lo = block K-1)
+  float hi[RT], lo[RT];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int k = 0; k < RT; ++k) { hi[k] = 0.f; lo[k] = 0.f; }
+  }
+  __device__ __forceinline__ void add(int r, int w, float v) { const int d = r - w; if (d >= 1) hi[d - 1] += v; else lo[RT - 1 + d] += v; }
+  // after a step: block K (hi) is finished; afterwards hi <- lo, lo <- 0
+  __device__ __forceinline__ void flush_step(float* row, int K, int RL) {
+#pragma unroll
+    for (int k = 0; k < RT; ++k) { const int mm = RT * K + k; if (mm < RL) atomicAdd(row + mm, hi[k]); hi[k] = lo[k]; lo[k] = 0.f; }
+  }
+  __device__ __forceinline__ void flush_end(float* row, int K, int RL) {     // remaining block K (now in hi)
+#pragma unroll
+    for (int k = 0; k < RT; ++k) { const int mm = RT * K + k; if (mm >= 0 && mm < RL) atomicAdd(row + mm, hi[k]); }
+  }
+};
+template <int RT>
+struct AccB {            // pairs index  walk - own + L - 1 ; shifted slots x = m + 1 (lo = block K-1, hi = block K)
+  float lo[RT], hi[RT];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int k = 0; k < RT; ++k) { hi[k] = 0.f; lo[k] = 0.f; }
+  }
+  __device__ __forceinline__ void add(int r, int w, float v) { const int d = w - r; if (d >= 0) hi[d] += v; else lo[RT + d] += v; }
+  // after a step: block K-1 (lo) is finished; afterwards lo <- hi, hi <- 0
+  __device__ __forceinline__ void flush_step(float* row, int K, int RL) {
+#pragma unroll
+    for (int k = 0; k < RT; ++k) { const int mm = RT * (K - 1) + k - 1; if (mm >= 0 && mm < RL) atomicAdd(row + mm, lo[k]); lo[k] = hi[k]; hi[k] = 0.f; }
+  }
+  __device__ __forceinline__ void flush_end(float* row, int K, int RL) {     // remaining block K (now in lo)
+#pragma unroll
+    for (int k = 0; k < RT; ++k) { const int mm = RT * K + k - 1; if (mm >= 0 && mm < RL) atomicAdd(row + mm, lo[k]); }
+  }
+};
+
 struct Bwd2Smem {
   float *ca, *cb, *wsim, *sA, *sB, *sC, *oA, *oB, *oC, *red, *Yn, *Rp, *Rs, *dOs, *Dl, *lses;
 };
@@ -40,12 +80,14 @@ k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stat
        const float* __restrict__ yraw, const float* __restrict__ oraw, const float* __restrict__ lse,
        const float* __restrict__ gs, float* __restrict__ dyh, int SPB, int segw) {
   constexpr int GP = 2 * D, NO = POS ? 2 : 1;
+  constexpr bool FOLD = POS && MODE == 1 && D <= 2;     // d relative accumulated inside the row pass (register budget: D <= 2)
   extern __shared__ __align__(16) float sm[];
   const int C = m.C, L = m.L, LP = m.LP, NOC = NO * C, RP = rel_pitch(L), LB = L / RT;
   const int b0 = blockIdx.x * SPB, grp = b0 / m.Bg;
-  // MODE 1: y = 0 rows, 1 columns, 2.. diagonals (the scalar diagonal walk is split over NDS CTAs)
-  const int phase = MODE == 0 ? 0 : ((int)blockIdx.y < 2 ? (int)blockIdx.y : 2);
-  const int dsplit = (int)blockIdx.y - 2, nds = (int)gridDim.y - 2;
+  // MODE 1: CTA y = 0 does the row pass then the column pass on ONE staging of the strips (the kernel is
+  // L2-staging bound, profiles/r1_notes.md); y >= 1 are the diagonal-walk CTAs (d relative), split nds ways
+  const bool diag_cta = MODE == 1 && blockIdx.y >= 1;
+  const int dsplit = (int)blockIdx.y - 1, nds = (int)gridDim.y - 1;
   const int nrel = POS ? 2 * GP * (2 * L - 1) : 0;
   const int nred = MODE == 0 ? 24 : 4 * C + nrel;
   Bwd2Smem s = carve2(m, sm, SPB, nred);
@@ -119,7 +161,8 @@ k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stat
   }
   __syncthreads();
 
-  const int nitems = (MODE == 1 && phase == 2) ? 0 : SPB * MT_G * LB;
+  const int nitems = diag_cta ? 0 : SPB * MT_G * LB;
+  for (int phase = 0; phase < (MODE == 0 ? 1 : 2); ++phase)
   for (int base = 0; base < nitems; base += blockDim.x) {
     const int item = base + threadIdx.x;
     const bool act = item < nitems;
@@ -160,6 +203,13 @@ k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stat
       for (int c = 0; c < D; ++c)
 #pragma unroll
         for (int r = 0; r < RT; ++r) dq[c][r] = 0.f;
+      AccA<RT> aRq[FOLD ? D : 1]; AccB<RT> aRk[FOLD ? D : 1]; AccA<RT> aRv[FOLD ? GP : 1];
+      if (FOLD) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) { aRq[c].zero(); aRk[c].zero(); }
+#pragma unroll
+        for (int c = 0; c < GP; ++c) aRv[c].zero();
+      }
       for (int wb = 0; wb < LB; ++wb) {
         float kk[D][RT], vv[GP][RT];
 #pragma unroll
@@ -196,14 +246,35 @@ k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stat
                 dq[c][r] = fmaf(dSqk, kk[c][w], dq[c][r]);
                 if (POS) dq[c][r] = fmaf(dSqr, wq[c].get(r, w), dq[c][r]);
               }
+              if (FOLD && act) {
+                const float dSkr = fmaf(Akr, dZ, fmaf(Ckr, skr, Bkr));
+#pragma unroll
+                for (int c = 0; c < D; ++c) { aRq[c].add(r, w, dSqr * q[c][r]); aRk[c].add(r, w, dSkr * kk[c][w]); }
+#pragma unroll
+                for (int c = 0; c < GP; ++c) aRv[c].add(r, w, P * dse[c][r]);
+              }
             }
           }
+        if (FOLD) {      // the block that just left the window is complete for this thread: flush it
+          const int RL = 2 * L - 1;
+#pragma unroll
+          for (int c = 0; c < D; ++c) { aRq[c].flush_step(dRs + c * RL, KA0 - wb, RL); aRk[c].flush_step(dRs + (D + c) * RL, KB0 + wb, RL); }
+#pragma unroll
+          for (int c = 0; c < GP; ++c) aRv[c].flush_step(dRs + (GP + c) * RL, KA0 - wb, RL);
+        }
         if (POS && wb + 1 < LB) {
 #pragma unroll
           for (int c = 0; c < D; ++c) { wq[c].advance(s.Rp + c * RP, KA0 - wb - 1); wk[c].advance(s.Rs + (D + c) * RP, KB0 + wb + 1); }
 #pragma unroll
           for (int c = 0; c < GP; ++c) wv[c].advance(s.Rp + (GP + c) * RP, KA0 - wb - 1);
         }
+      }
+      if (FOLD) {
+        const int RL = 2 * L - 1;
+#pragma unroll
+        for (int c = 0; c < D; ++c) { aRq[c].flush_end(dRs + c * RL, KA0 - LB, RL); aRk[c].flush_end(dRs + (D + c) * RL, KB0 + LB - 1, RL); }
+#pragma unroll
+        for (int c = 0; c < GP; ++c) aRv[c].flush_end(dRs + (GP + c) * RL, KA0 - LB, RL);
       }
       if (MODE == 0) {
         if (!act) { t0 = t1 = t2 = 0.f; }
@@ -234,7 +305,7 @@ k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stat
           if (act && (threadIdx.x & (segw - 1)) == 0) { atomicAdd(s.red + ch * 2, s1); atomicAdd(s.red + ch * 2 + 1, s2); }
         }
       }
-    } else if (phase == 1) {
+    } else {
       // ------------------------------------------------------------ thread owns columns j = RT*t + r
       float kc_[D][RT], vc_[GP][RT];
 #pragma unroll
@@ -325,7 +396,7 @@ k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stat
     }
   }
   // ------------------------------------------------------------ diagonals (d relative), scalar walk
-  if (MODE == 1 && POS && phase == 2) {
+  if (POS && !FOLD && diag_cta) {
     const int RL = 2 * L - 1, nd = SPB * MT_G * RL;
     const int per = (nd + nds - 1) / nds, i0 = dsplit * per, i1 = i0 + per < nd ? i0 + per : nd;
     for (int item = i0 + threadIdx.x; item < i1; item += blockDim.x) {
@@ -373,15 +444,12 @@ k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stat
     if (threadIdx.x < m.nt * MT_G) MT_GADD(m, bs + m.b_sim_t + threadIdx.x, (double)s.red[threadIdx.x]);
     if (last_cta_done(bcnt + 1, gridDim.x)) fin_bwd_sim(m, p, stats, bstats, bcoef);
   } else {
-    if (phase < 2)
+    if (!diag_cta)
       for (int ch = threadIdx.x; ch < 2 * C; ch += blockDim.x) {
-        const int r = ch % (2 * GP);
-        if ((r < D) == (phase == 0)) {
-          MT_GADD(m, bs + m.b_qkv_s1 + ch, (double)s.red[ch * 2]);
-          MT_GADD(m, bs + m.b_qkv_s2 + ch, (double)s.red[ch * 2 + 1]);
-        }
+        MT_GADD(m, bs + m.b_qkv_s1 + ch, (double)s.red[ch * 2]);
+        MT_GADD(m, bs + m.b_qkv_s2 + ch, (double)s.red[ch * 2 + 1]);
       }
-    if (POS && phase == 2)
+    if (POS && (FOLD ? !diag_cta : diag_cta))
       for (int k = threadIdx.x; k < nrel; k += blockDim.x) MT_GADD(m, gr.drelative + k, dRs[k]);
     // last CTA of all passes: bn_qkv backward coefficients for the projection GEMMs + every BN / gate gradient
     if (last_cta_done(bcnt + 2, gridDim.x * gridDim.y)) {
@@ -408,7 +476,7 @@ static int launch_b(const Dims& m, const MtAxialParams& p, const MtAxialGrads& g
   if (smem > 32 * 1024 &&
       cudaFuncSetAttribute(k_bwd2<D, POS, RT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return -1;
-  const dim3 grid(m.B / spb, MODE == 0 ? 1 : (POS ? 2 + 4 : 2));      // rows, columns, 4 x diagonals
+  const dim3 grid(m.B / spb, (MODE == 1 && POS && D > 2) ? 1 + 2 : 1);  // rows+columns (+ d relative when D <= 2); else 2 diagonal CTAs
   k_bwd2<D, POS, RT, MODE><<<grid, 128, smem, st>>>(m, p, gr, stats, bstats, coef, bcoef, bcnt, yraw, oraw, lse, gs, dyh,
                                                     spb, segw);
   return 1;
