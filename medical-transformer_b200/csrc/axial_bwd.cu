@@ -408,7 +408,6 @@ int axial_backward_launch(const Dims& m, const MtAxialParams& p, const float* x,
   int nl = 0;
   if (mask == 0x1f) {
   if (cudaMemsetAsync(ws + m.ws_bstats, 0, m.ws_zero_bytes, st) != cudaSuccess) return -1;
-  if (gr.dw_qkv && cudaMemsetAsync(gr.dw_qkv, 0, sizeof(float) * 2 * (size_t)m.C * m.C, st) != cudaSuccess) return -1;
   if (m.pos && gr.drelative &&
       cudaMemsetAsync(gr.drelative, 0, sizeof(float) * 2 * (size_t)m.gp * (2 * m.L - 1), st) != cudaSuccess)
     return -1;

@@ -317,17 +317,18 @@ int launch_proj(const Dims& m, const MtAxialParams& p, const float* x, float* yr
   return 1;
 }
 
+cudaStream_t mt_side_fork(cudaStream_t main_stream);
+void mt_side_join(cudaStream_t main_stream, cudaStream_t forked);
+
 int launch_bwd_proj(const Dims& m, const MtAxialParams& p, const MtAxialGrads& gr, const float* x, const float* bcoef,
                     const float* yraw, const float* dyh, cudaStream_t st) {
   int TS, TL, nTL, nTS;
   proj_tiling(m, TS, TL, nTL, nTS);
   const int ntiles = m.ngroups * nTS * nTL;
+  cudaStream_t sd = st;
   {
-    dim3 grid(ntiles, (m.C + 63) / 64);
-    const size_t smem = sizeof(float) * (2 * 16 * TILE_LD + 6 * (size_t)m.C + 64 * 65);
-    k_bwd_dx<<<grid, 256, smem, st>>>(m, p, gr, bcoef, yraw, dyh, TS, TL, nTS * nTL, nTL);
-  }
-  {
+    // dW only depends on what k_bwd2 left behind, exactly like dX: run it on the forked side stream
+    sd = gr.dw_qkv ? mt_side_fork(st) : st;          // fork BEFORE dX is enqueued so the two overlap
     const int mn = ((2 * m.C + 63) / 64) * ((m.C + 63) / 64);
     int ksplit = (148 + mn - 1) / mn;                 // fill the 148 SMs: CTAs = Mtiles * Ntiles * ksplit
     if (ksplit > ntiles) ksplit = ntiles;
@@ -335,7 +336,14 @@ int launch_bwd_proj(const Dims& m, const MtAxialParams& p, const MtAxialGrads& g
     const size_t smem = sizeof(float) * (2 * 64 * TILE_LD + 6 * (size_t)m.C);
     static bool once = (cudaFuncSetAttribute(k_bwd_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), true);
     (void)once;
-    k_bwd_dw<<<grid, 256, smem, st>>>(m, gr, x, bcoef, yraw, dyh, TS, TL, nTS * nTL, nTL, ntiles);
+    if (gr.dw_qkv) cudaMemsetAsync(gr.dw_qkv, 0, sizeof(float) * 2 * (size_t)m.C * m.C, sd);
+    k_bwd_dw<<<grid, 256, smem, sd>>>(m, gr, x, bcoef, yraw, dyh, TS, TL, nTS * nTL, nTL, ntiles);
   }
+  {
+    dim3 grid(ntiles, (m.C + 63) / 64);
+    const size_t smem = sizeof(float) * (2 * 16 * TILE_LD + 6 * (size_t)m.C + 64 * 65);
+    k_bwd_dx<<<grid, 256, smem, st>>>(m, p, gr, bcoef, yraw, dyh, TS, TL, nTS * nTL, nTL);
+  }
+  mt_side_join(st, sd);
   return 2;
 }

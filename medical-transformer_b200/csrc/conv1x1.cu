@@ -9,6 +9,8 @@
 #include "common.cuh"
 extern thread_local cudaError_t g_last_cuda;
 int mt_fail_msg(int code, const char* msg);
+cudaStream_t mt_side_fork(cudaStream_t main_stream);
+void mt_side_join(cudaStream_t main_stream, cudaStream_t forked);
 
 #define C1_LD 68
 struct C1Args { int N, Ci, Co, H, W, stride, Ho, Wo; };
@@ -195,20 +197,22 @@ int mt_conv1x1_backward(int N, int Ci, int Co, int H, int W, int stride, const f
   C1Args a{N, Ci, Co, H, W, stride, (H - 1) / stride + 1, (W - 1) / stride + 1};
   const long P = (long)N * a.Ho * a.Wo;
   cudaStream_t st = (cudaStream_t)stream;
-  if (dx) {
-    if (stride > 1) cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)N * Ci * H * W, st);
-    k_c1_dx<<<dim3((unsigned)((P + 63) / 64), (Ci + 63) / 64), 256, 0, st>>>(a, dy, w, dx);
-  }
+  cudaStream_t sd = (dw && dx) ? mt_side_fork(st) : st;          // dW next to dX, not behind it
   if (dw) {
-    cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Co * Ci, st);
+    cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Co * Ci, sd);
     const int ntiles = (int)((P + 63) / 64), mn = ((Co + 63) / 64) * ((Ci + 63) / 64);
     int ksplit = (148 + mn - 1) / mn;
     if (ksplit > ntiles) ksplit = ntiles;
     const size_t smem = sizeof(float) * 2 * 64 * C1_LD;
     static bool once = (cudaFuncSetAttribute(k_c1_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), true);
     (void)once;
-    k_c1_dw<<<dim3((Co + 63) / 64, (Ci + 63) / 64, ksplit), 256, smem, st>>>(a, dy, x, dw, ntiles);
+    k_c1_dw<<<dim3((Co + 63) / 64, (Ci + 63) / 64, ksplit), 256, smem, sd>>>(a, dy, x, dw, ntiles);
   }
+  if (dx) {
+    if (stride > 1) cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)N * Ci * H * W, st);
+    k_c1_dx<<<dim3((unsigned)((P + 63) / 64), (Ci + 63) / 64), 256, 0, st>>>(a, dy, w, dx);
+  }
+  mt_side_join(st, sd);
   g_last_cuda = cudaGetLastError();
   return g_last_cuda == cudaSuccess ? MT_OK : mt_fail_msg(MT_ERR_CUDA, "mt_conv1x1_backward: launch failed");
 }

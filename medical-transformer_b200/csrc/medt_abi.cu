@@ -2,6 +2,7 @@
 // No torch types, no exceptions, no allocation, no device synchronisation.
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 int axial_forward_launch(const Dims& m, const MtAxialParams& p, const float* x, float* out, char* saved,
@@ -18,6 +19,43 @@ static int fail(int code, const char* msg) {
   return code;
 }
 int mt_fail_msg(int code, const char* msg) { return fail(code, msg); }
+// ---- fork/join side stream (per thread and device): independent kernels of one call (the weight-gradient
+// GEMMs next to the input-gradient GEMMs) overlap instead of queueing behind each other.  Event fork/join
+// is capturable, so the overlap survives inside the training-step CUDA graph.
+struct SideStream { cudaStream_t s; cudaEvent_t fork, join; bool ok; };
+static thread_local SideStream g_side[32] = {};
+static SideStream* side_for_current_device() {
+  static const bool disabled = getenv("MT_NO_SIDE_STREAM") != nullptr;
+  if (disabled) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return nullptr;
+  SideStream& ss = g_side[dev];
+  if (!ss.ok) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;      // never create resources while capturing
+    if (cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    (void)cs;
+    ss.ok = true;
+  }
+  return &ss;
+}
+// returns the stream to launch the forked work on (== main when no side stream is available)
+cudaStream_t mt_side_fork(cudaStream_t main_stream) {
+  SideStream* ss = side_for_current_device();
+  if (!ss) return main_stream;
+  if (cudaEventRecord(ss->fork, main_stream) != cudaSuccess) return main_stream;
+  if (cudaStreamWaitEvent(ss->s, ss->fork, 0) != cudaSuccess) return main_stream;
+  return ss->s;
+}
+void mt_side_join(cudaStream_t main_stream, cudaStream_t forked) {
+  if (forked == main_stream) return;
+  SideStream* ss = side_for_current_device();
+  if (!ss) return;
+  cudaEventRecord(ss->join, forked);
+  cudaStreamWaitEvent(main_stream, ss->join, 0);
+}
+
 static int fail_cuda(const char* where) {
   cudaError_t e = g_last_cuda != cudaSuccess ? g_last_cuda : cudaGetLastError();
   snprintf(g_err, sizeof(g_err), "%s: CUDA error %d (%s)", where, (int)e, cudaGetErrorString(e));
