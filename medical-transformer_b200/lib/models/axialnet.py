@@ -14,6 +14,7 @@ Reference map (file:line in /root/reference/lib/models/axialnet.py):
 There is no CPU path: forward on a non-CUDA tensor raises (BASELINE north_star: "no CPU
 fallback")."""
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -300,16 +301,41 @@ class medt_net(_ShellBase):
 
     def _forward_impl(self, x):
         xin = x
+        # The global and the local branch are independent until the merge: the local branch runs on a
+        # second CUDA stream (autograd replays its backward on that stream too), so the two chains of
+        # microsecond-scale kernels overlap on the 148 SMs.  Fork/join is capturable in the step graph.
+        cur = torch.cuda.current_stream(x.device) if x.is_cuda else None
+        side = self._side_stream(x.device) if x.is_cuda else None
+        if side is not None:
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                loc = self._local_branch(xin)
         x = self._stem(x, (self.conv1, self.conv2, self.conv3), (self.bn1, self.bn2, self.bn3))
         x1 = self.layer1(x)
         x2 = self.layer2(x1)
         x = _up_relu(self.decoder4, x2, x1)
         x = _up_relu(self.decoder5, x)
-        side = self._patch * GRID
+        if side is not None:
+            cur.wait_stream(side)
+            loc.record_stream(cur)
+        else:
+            loc = self._local_branch(xin)       # raises: no CPU path
+        side_len = self._patch * GRID
         x_loc = x.clone()                       # outside the 128x128 patch grid x_loc stays == x (:658,:700)
-        x_loc[:, :, :side, :side] = self._local_branch(xin)
+        x_loc[:, :, :side_len, :side_len] = loc
         x = F.relu(self.decoderf(x + x_loc))
         return self.adjust(F.relu(x))
+
+    def _side_stream(self, device):
+        if os.environ.get("MEDT_NO_BRANCH_STREAM"):
+            return None
+        st = getattr(self, "_streams", None)
+        if st is None:
+            st = self._streams = {}
+        key = torch.device(device).index
+        if key not in st:
+            st[key] = torch.cuda.Stream(device=device)
+        return st[key]
 
     def forward(self, x):
         return self._forward_impl(x)
