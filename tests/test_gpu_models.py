@@ -170,3 +170,26 @@ def test_long_sequence_L256_matches_oracle():
     assert rel_err(out.detach().cpu().numpy(), out_ref) < 1e-4
     assert rel_err(xt.grad.cpu().numpy(), gref["dx"]) < 2e-3
     assert rel_err(mod.relative.grad.cpu().numpy(), gref["drelative"]) < 2e-3
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_dataparallel_two_gpus_like_train_py():
+    """train.py:104-108 wraps the model in nn.DataParallel(device_ids=[0,1]) (one thread per GPU in one
+    process): the C ABI must be re-entrant and the modules replicable.  Eval-mode outputs of the two
+    replicas must equal the single-GPU forward; a train-mode forward/backward must produce finite grads."""
+    m = build_filled_model("gated", 64, device="cuda")
+    x = torch.tensor(fill.image_batch(4, 3, 64), dtype=torch.float32, device="cuda")
+    y = torch.tensor(fill.mask_batch(4, 64), device="cuda")
+    m.eval()
+    with torch.no_grad():
+        ref = m(x)
+    dp = torch.nn.DataParallel(m, device_ids=[0, 1]).cuda()
+    with torch.no_grad():
+        got = dp(x)
+    assert torch.allclose(got, ref, atol=1e-5, rtol=1e-5)
+    dp.train()
+    loss = torch.nn.functional.cross_entropy(dp(x), y)
+    loss.backward()
+    assert torch.isfinite(loss).item()
+    assert all(torch.isfinite(p.grad).all().item() for p in m.parameters() if p.grad is not None)
+    assert all(k.startswith("module.") for k in dp.state_dict())
