@@ -20,18 +20,10 @@ struct AccA {            // pairs index  own - walk + L - 1 ; slot layout of Win
     for (int k = 0; k < RT; ++k) { hi[k] = 0.f; lo[k] = 0.f; }
   }
   __device__ __forceinline__ void add(int r, int w, float v) { const int d = r - w; if (d >= 1) hi[d - 1] += v; else lo[RT - 1 + d] += v; }
-  // after a step block K (hi) is finished for this thread.  The thread one lane up has the same block in its
-  // `lo`: hand the finished partial sums over with a shuffle instead of flushing them (shared-memory atomics
-  // here cost more than the whole pair loop: profiles/r1_notes.md).  Only the last lane of a segment flushes.
-  __device__ __forceinline__ void pass_step(bool first, bool last, float* row, int K, int RL) {
+  // after a step: block K (hi) is finished; afterwards hi <- lo, lo <- 0
+  __device__ __forceinline__ void flush_step(float* row, int K, int RL) {
 #pragma unroll
-    for (int k = 0; k < RT; ++k) {
-      const float fin = hi[k];
-      float recv = __shfl_up_sync(0xffffffffu, fin, 1);
-      if (first) recv = 0.f;
-      if (last) { const int mm = RT * K + k; if (mm < RL) atomicAdd(row + mm, fin); }
-      hi[k] = lo[k] + recv; lo[k] = 0.f;
-    }
+    for (int k = 0; k < RT; ++k) { const int mm = RT * K + k; if (mm < RL) atomicAdd(row + mm, hi[k]); hi[k] = lo[k]; lo[k] = 0.f; }
   }
   __device__ __forceinline__ void flush_end(float* row, int K, int RL) {     // remaining block K (now in hi)
 #pragma unroll
@@ -46,16 +38,10 @@ struct AccB {            // pairs index  walk - own + L - 1 ; shifted slots x = 
     for (int k = 0; k < RT; ++k) { hi[k] = 0.f; lo[k] = 0.f; }
   }
   __device__ __forceinline__ void add(int r, int w, float v) { const int d = w - r; if (d >= 0) hi[d] += v; else lo[RT + d] += v; }
-  // after a step block K-1 (lo) is finished for this thread; the next lane continues it as its `lo`
-  __device__ __forceinline__ void pass_step(bool first, bool last, float* row, int K, int RL) {
+  // after a step: block K-1 (lo) is finished; afterwards lo <- hi, hi <- 0
+  __device__ __forceinline__ void flush_step(float* row, int K, int RL) {
 #pragma unroll
-    for (int k = 0; k < RT; ++k) {
-      const float fin = lo[k];
-      float recv = __shfl_up_sync(0xffffffffu, fin, 1);
-      if (first) recv = 0.f;
-      if (last) { const int mm = RT * (K - 1) + k - 1; if (mm >= 0 && mm < RL) atomicAdd(row + mm, fin); }
-      lo[k] = hi[k] + recv; hi[k] = 0.f;
-    }
+    for (int k = 0; k < RT; ++k) { const int mm = RT * (K - 1) + k - 1; if (mm >= 0 && mm < RL) atomicAdd(row + mm, lo[k]); lo[k] = hi[k]; hi[k] = 0.f; }
   }
   __device__ __forceinline__ void flush_end(float* row, int K, int RL) {     // remaining block K (now in lo)
 #pragma unroll
@@ -175,7 +161,7 @@ k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stat
   }
   __syncthreads();
 
-  const int nitems = (diag_cta || (m.dbg & 4)) ? 0 : SPB * MT_G * LB;   // dbg bit2: fixed-cost experiment
+  const int nitems = diag_cta ? 0 : SPB * MT_G * LB;
   for (int phase = 0; phase < (MODE == 0 ? 1 : 2); ++phase)
   for (int base = 0; base < nitems; base += blockDim.x) {
     const int item = base + threadIdx.x;
@@ -269,16 +255,12 @@ k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stat
               }
             }
           }
-        if (FOLD) {      // the block that just left the window is complete for this thread: hand it to lane + 1
+        if (FOLD) {      // the block that just left the window is complete for this thread: flush it
           const int RL = 2 * L - 1;
-          const bool first = (threadIdx.x & (segw - 1)) == 0, last = (threadIdx.x & (segw - 1)) == segw - 1;
 #pragma unroll
-          for (int c = 0; c < D; ++c) {
-            aRq[c].pass_step(first, last, dRs + c * RL, KA0 - wb, RL);
-            aRk[c].pass_step(first, last, dRs + (D + c) * RL, KB0 + wb, RL);
-          }
+          for (int c = 0; c < D; ++c) { aRq[c].flush_step(dRs + c * RL, KA0 - wb, RL); aRk[c].flush_step(dRs + (D + c) * RL, KB0 + wb, RL); }
 #pragma unroll
-          for (int c = 0; c < GP; ++c) aRv[c].pass_step(first, last, dRs + (GP + c) * RL, KA0 - wb, RL);
+          for (int c = 0; c < GP; ++c) aRv[c].flush_step(dRs + (GP + c) * RL, KA0 - wb, RL);
         }
         if (POS && wb + 1 < LB) {
 #pragma unroll
@@ -460,7 +442,7 @@ k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stat
   double* bs = stat_slot(m, bstats, grp, m.nstat_b, blockIdx.x);
   if (MODE == 0) {
     if (threadIdx.x < m.nt * MT_G) MT_GADD(m, bs + m.b_sim_t + threadIdx.x, (double)s.red[threadIdx.x]);
-    if (last_cta_done(bcnt + 1 * MT_TICKET_STRIDE, gridDim.x)) fin_bwd_sim(m, p, stats, bstats, bcoef);
+    if (last_cta_done(bcnt + 1, gridDim.x)) fin_bwd_sim(m, p, stats, bstats, bcoef);
   } else {
     if (!diag_cta)
       for (int ch = threadIdx.x; ch < 2 * C; ch += blockDim.x) {
@@ -470,7 +452,7 @@ k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stat
     if (POS && (FOLD ? !diag_cta : diag_cta))
       for (int k = threadIdx.x; k < nrel; k += blockDim.x) MT_GADD(m, gr.drelative + k, dRs[k]);
     // last CTA of all passes: bn_qkv backward coefficients for the projection GEMMs + every BN / gate gradient
-    if (last_cta_done(bcnt + 2 * MT_TICKET_STRIDE, gridDim.x * gridDim.y)) {
+    if (last_cta_done(bcnt + 2, gridDim.x * gridDim.y)) {
       fin_bwd_qkv(m, p, stats, bstats, bcoef);
       bwd_param_grads(m, p, gr, stats, bstats);
     }

@@ -194,7 +194,7 @@ k_bwd_simstats(Dims m, MtAxialParams p, const double* __restrict__ stats, double
   __syncthreads();
   if (threadIdx.x < m.nt * MT_G)
     MT_GADD(m, stat_slot(m, bstats, grp, m.nstat_b, blockIdx.x) + m.b_sim_t + threadIdx.x, (double)s.red[threadIdx.x]);
-  if (last_cta_done(bcnt + 1 * MT_TICKET_STRIDE, gridDim.x)) fin_bwd_sim(m, p, stats, bstats, bcoef);
+  if (last_cta_done(bcnt + 1, gridDim.x)) fin_bwd_sim(m, p, stats, bstats, bcoef);
 }
 
 // ============================================================================ k_bwd_attn
@@ -360,7 +360,7 @@ k_bwd_attn(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ 
   if (POS && phase == 2)
     for (int k = threadIdx.x; k < nrel; k += blockDim.x) MT_GADD(m, drel + k, dRs[k]);
   // last CTA: bn_qkv backward coefficients for the projection GEMMs + every BN / gate parameter gradient
-  if (last_cta_done(bcnt + 2 * MT_TICKET_STRIDE, gridDim.x * gridDim.y)) {
+  if (last_cta_done(bcnt + 2, gridDim.x * gridDim.y)) {
     fin_bwd_qkv(m, p, stats, bstats, bcoef);
     bwd_param_grads(m, p, gr, stats, bstats);
   }

@@ -94,7 +94,7 @@ k_sim_stats(Dims m, MtAxialParams p, const float* __restrict__ yraw, double* __r
     MT_GADD(m, st + m.f_sim_sum + threadIdx.x, (double)red[threadIdx.x * 2 + 0]);
     MT_GADD(m, st + m.f_sim_sq + threadIdx.x, (double)red[threadIdx.x * 2 + 1]);
   }
-  if (last_cta_done(cnt + 1 * MT_TICKET_STRIDE, gridDim.x)) fin_sim(m, p, stats, coef);   // softmax weights + bn_similarity running stats
+  if (last_cta_done(cnt + 1, gridDim.x)) fin_sim(m, p, stats, coef);   // softmax weights + bn_similarity running stats
 }
 
 // ============================================================================ k_attn
@@ -196,7 +196,7 @@ k_attn(Dims m, MtAxialParams p, const float* __restrict__ yraw, double* __restri
       MT_GADD(m, st + m.f_out_sq + ch, (double)red[ch * 2 + 1]);
     }
   }
-  if (last_cta_done(cnt + 2 * MT_TICKET_STRIDE, gridDim.x)) fin_out(m, p, stats, coef);      // bn_output coefficients + running stats
+  if (last_cta_done(cnt + 2, gridDim.x)) fin_out(m, p, stats, coef);      // bn_output coefficients + running stats
 }
 
 // ============================================================================ host launchers

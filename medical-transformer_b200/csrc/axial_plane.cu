@@ -98,7 +98,7 @@ __device__ __forceinline__ void gather_reduce(const Dims& m, const MtAxialParams
     else if (threadIdx.x == 1) MT_GADD(m, bs + m.b_out_s2 + c * m.no, (double)t);
     else if (m.no == 2) MT_GADD(m, bs + m.b_out_s2 + c * m.no + 1, (double)t);
   }
-  if (last_cta_done(bcnt + 0 * MT_TICKET_STRIDE, gridDim.x * gridDim.y * gridDim.z)) fin_bwd_out(m, p, stats, bstats, bcoef);
+  if (last_cta_done(bcnt + 0, gridDim.x * gridDim.y * gridDim.z)) fin_bwd_out(m, p, stats, bstats, bcoef);
 }
 
 // grid (splits, C, groups): a CTA walks a chunk of the (group, channel) slab of npg*H*W full-resolution

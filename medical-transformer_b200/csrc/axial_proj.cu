@@ -135,7 +135,7 @@ k_proj(Dims m, MtAxialParams p, const float* __restrict__ x, const float* __rest
   }
   // last CTA: bn_qkv coefficients (+ running stats); in eval mode also the similarity weights,
   // because k_sim_stats is not launched then
-  if (last_cta_done(cnt + 0 * MT_TICKET_STRIDE, gridDim.x * gridDim.y)) {
+  if (last_cta_done(cnt + 0, gridDim.x * gridDim.y)) {
     fin_qkv(m, p, stats, coef);
     if (!m.training) fin_sim(m, p, stats, coef);
   }

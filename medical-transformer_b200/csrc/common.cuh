@@ -9,8 +9,6 @@
 
 #define MT_G 8              // heads: fixed by the reference (axialnet.py:400)
 #define MT_LOG2E 1.4426950408889634f
-#define MT_TICKET_WAYS 16
-#define MT_TICKET_STRIDE 32   // uints per ticket set (top level + sub-counters, padded)
 #define MT_NREP 8           // max replicated fp64 accumulator slots (CTA picks blockIdx % nrep): cuts same-address atomic
                             // serialisation; used only when there are few statistic groups (m.nrep)
 
@@ -71,7 +69,7 @@ static inline bool make_dims(const MtAxialDesc* d, Dims& m) {
   m.cb_o = 0; m.cb_s = 3 * m.no * C; m.cb_q = m.cb_s + 3 * m.nt * MT_G; m.ncoef_b = m.cb_q + 6 * C;
   size_t off = 0;
   m.sv_stats = off; off += sizeof(double) * (size_t)m.nrep * m.ngroups * m.nstat_f;
-  m.sv_cnt = off;   off = mt_align(off + 4 * sizeof(unsigned) * MT_TICKET_STRIDE);          // CTA-done tickets, zeroed together with the accumulators
+  m.sv_cnt = off;   off = mt_align(off + 64);          // CTA-done tickets, zeroed together with the accumulators
   m.sv_zero_bytes = off;
   m.sv_coef = off;  off = mt_align(off + sizeof(float) * (size_t)m.ngroups * m.ncoef_f);
   m.sv_yraw = off;  off = mt_align(off + sizeof(float) * (size_t)m.B * 2 * C * m.L);
@@ -80,7 +78,7 @@ static inline bool make_dims(const MtAxialDesc* d, Dims& m) {
   m.sv_bytes = off;
   off = 0;
   m.ws_bstats = off; off += sizeof(double) * (size_t)m.nrep * m.ngroups * m.nstat_b;
-  m.ws_cnt = off;    off = mt_align(off + 4 * sizeof(unsigned) * MT_TICKET_STRIDE);
+  m.ws_cnt = off;    off = mt_align(off + 64);
   m.ws_zero_bytes = off;
   m.ws_coef = off;   off = mt_align(off + sizeof(float) * (size_t)m.ngroups * m.ncoef_b);
   m.ws_gs = off;     off = mt_align(off + sizeof(float) * (size_t)m.B * C * m.L);
@@ -204,25 +202,11 @@ __device__ __forceinline__ void ema_update(const Dims& m, float* rm, float* rv, 
 // "last CTA done": after a CTA has issued its global accumulations it takes a ticket; the CTA
 // that draws the last one sees every accumulation (fence + L2 atomics) and finalises.
 __device__ __forceinline__ bool last_cta_done(unsigned* counter, unsigned total) {
-  // two-level tickets: a same-address atomic per CTA serialises at the L2 (~20 ns each: 256-1024 CTAs cost
-  // 5-20 us); CTAs first draw from one of MT_TICKET_WAYS sub-counters, the CTA completing a sub-counter draws
-  // from the top-level one.  counter[0] = top level, counter[1..WAYS] = sub-counters (all zeroed by the memset).
   __shared__ int is_last;
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned id = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-    const unsigned ways = total < MT_TICKET_WAYS ? total : MT_TICKET_WAYS;
-    const unsigned b = id % ways, quota = (total - b + ways - 1) / ways;
-    int last = 0;
-    if (atomicAdd(counter + 1 + b, 1u) == quota - 1u) {
-      __threadfence();
-      last = atomicAdd(counter, 1u) == ways - 1u;
-    }
-    is_last = last;
-  }
+  if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == total - 1u);
   __syncthreads();
-  if (is_last) __threadfence();
   return is_last != 0;
 }
 
