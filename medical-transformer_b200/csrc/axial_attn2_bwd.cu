@@ -161,7 +161,7 @@ k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stat
   }
   __syncthreads();
 
-  const int nitems = diag_cta ? 0 : SPB * MT_G * LB;
+  const int nitems = (diag_cta || (m.dbg & 4)) ? 0 : SPB * MT_G * LB;   // dbg bit2: fixed-cost experiment
   for (int phase = 0; phase < (MODE == 0 ? 1 : 2); ++phase)
   for (int base = 0; base < nitems; base += blockDim.x) {
     const int item = base + threadIdx.x;

@@ -38,7 +38,7 @@ k_attn2(Dims m, MtAxialParams p, const float* __restrict__ yraw, double* __restr
   else stage_rows(yraw + (size_t)b0 * 2 * C * L, SPB * 2 * C, L, LP, ca, cb, 2 * C, Yn);
   __syncthreads();
 
-  const int nitems = SPB * MT_G * LB;
+  const int nitems = (m.dbg & 4) ? 0 : SPB * MT_G * LB;      // MT_DEBUG_FLAGS bit2: skip the main loop (fixed-cost experiment)
   for (int base = 0; base < nitems; base += blockDim.x) {
     const int item = base + threadIdx.x;
     const bool act = item < nitems;
@@ -205,6 +205,9 @@ static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 // RT for this shape, or 0 when the v2 layout does not apply (falls back to the v1 kernels)
 int attn2_rt(const Dims& m) {
   int rt = m.d == 1 ? 4 : (m.d == 2 || m.d == 4 ? 2 : 0);
+  // MT_FORCE_RT (developer): RT for the d = 1 layers.  Measured: RT 2 vs 4 is a wash at 128 px (profiles/r1_notes.md)
+  static const int force = getenv("MT_FORCE_RT") ? atoi(getenv("MT_FORCE_RT")) : 0;
+  if ((force == 2 || force == 4) && m.d == 1) rt = force;
   if (rt == 4 && (m.L % 4 || !is_pow2(m.L / 4))) rt = 2;
   if (rt == 2 && (m.L % 2 || !is_pow2(m.L / 2))) rt = 0;
   if (rt && m.L / rt > 0 && (m.LP % rt)) rt = 0;
