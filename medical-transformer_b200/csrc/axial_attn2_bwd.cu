@@ -1,7 +1,7 @@
 // axial_attn2_bwd.cu -- register-tiled backward attention passes (layout of axial_attn2.cuh):
 //   MODE 0  T[t,g] = sum dZ * S_t                       (bn_similarity backward needs it first)
 //   MODE 1  gradients; blockIdx.y picks the pass so the three run concurrently:
-//     y=0 rows:    dq[c,i] = sum_j dS_qk k[c,j] + dS_qr Rq[c,i-j]           (thread owns RT rows)
+//     y=0 rows, then columns on the same staging: dq[c,i] = sum_j dS_qk k[c,j] + dS_qr Rq[c,i-j]           (thread owns RT rows)
 //     y=1 columns: dk[c,j] = sum_i dS_qk q[c,i] + dS_kr Rk[c,j-i] ; dv[c,j] = sum_i P dO_sv[c,i]
 //                                                                           (thread owns RT columns)
 //     y=2 diagonals: d relative[c, i-j+L-1] (one thread per diagonal, scalar walk)
@@ -80,7 +80,14 @@ k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stat
        const float* __restrict__ yraw, const float* __restrict__ oraw, const float* __restrict__ lse,
        const float* __restrict__ gs, float* __restrict__ dyh, int SPB, int segw) {
   constexpr int GP = 2 * D, NO = POS ? 2 : 1;
-  constexpr bool FOLD = POS && MODE == 1 && D <= 2;     // d relative accumulated inside the row pass (register budget: D <= 2)
+  // d relative: default = concurrent diagonal-walk CTAs (blockIdx.y >= 1).  -DMT_FOLD_DREL accumulates it inside the
+  // row pass instead (mirror window accumulators, no extra pair evaluations) -- measured 2.4 % slower at 128 px and
+  // 10 % slower at 512 px because of its bank-conflicted shared-memory atomics (profiles/r1_notes.md).
+#ifdef MT_FOLD_DREL
+  constexpr bool FOLD = POS && MODE == 1 && D <= 2;
+#else
+  constexpr bool FOLD = false;
+#endif
   extern __shared__ __align__(16) float sm[];
   const int C = m.C, L = m.L, LP = m.LP, NOC = NO * C, RP = rel_pitch(L), LB = L / RT;
   const int b0 = blockIdx.x * SPB, grp = b0 / m.Bg;
@@ -476,7 +483,11 @@ static int launch_b(const Dims& m, const MtAxialParams& p, const MtAxialGrads& g
   if (smem > 32 * 1024 &&
       cudaFuncSetAttribute(k_bwd2<D, POS, RT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return -1;
-  const dim3 grid(m.B / spb, (MODE == 1 && POS && D > 2) ? 1 + 2 : 1);  // rows+columns (+ d relative when D <= 2); else 2 diagonal CTAs
+#ifdef MT_FOLD_DREL
+  const dim3 grid(m.B / spb, (MODE == 1 && POS && D > 2) ? 1 + 2 : 1);
+#else
+  const dim3 grid(m.B / spb, (MODE == 1 && POS) ? 1 + 2 : 1);          // y = 0: rows then columns; y = 1, 2: diagonal walk
+#endif
   k_bwd2<D, POS, RT, MODE><<<grid, 128, smem, st>>>(m, p, gr, stats, bstats, coef, bcoef, bcnt, yraw, oraw, lse, gs, dyh,
                                                     spb, segw);
   return 1;
