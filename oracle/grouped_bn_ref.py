@@ -1,4 +1,7 @@
-"""BatchNorm2d with per-group batch statistics, for the batched LoGo local branch.
+"""CPU ORACLE (test infrastructure, NOT product code) -- plain-PyTorch BatchNorm2d with per-group batch
+statistics: the semantics the CUDA kernel mt_bn_act_forward must reproduce for the batched LoGo local branch.
+Only tests/ import it (tests/test_dropin.py pins it against 16 sequential nn.BatchNorm2d calls).
+
 
 The reference runs its 16 patches through the SAME BatchNorm modules one after another
 (axialnet.py:661-700), so each call normalises with that patch's statistics and applies one

@@ -58,8 +58,8 @@ def test_constructor_errors_match_reference():
 
 
 def test_grouped_bn_matches_sequential_calls():
-    """Host logic of the batched LoGo branch: grouped statistics == one BN call per patch."""
-    from medt_b200.grouped_bn import batch_norm_grouped
+    """Semantics of the batched LoGo branch (oracle side): grouped statistics == one BN call per patch."""
+    from oracle.grouped_bn_ref import batch_norm_grouped
     torch.manual_seed(0)
     x = torch.randn(12, 5, 4, 4, dtype=torch.float64)
     a, b = torch.nn.BatchNorm2d(5).double(), torch.nn.BatchNorm2d(5).double()

@@ -152,3 +152,39 @@ def test_wrong_length_raises_like_reference():
     mod = lib.models.axialnet.AxialAttention_dynamic(16, 16, groups=8, kernel_size=16).cuda()
     with pytest.raises(RuntimeError):
         mod(torch.randn(1, 16, 8, 8, device="cuda"))
+
+
+@pytest.mark.parametrize("variant,C,H,W,axis,stride", [("gated", 16, 6, 10, 0, 1), ("pos", 32, 12, 6, 1, 2),
+                                                      ("nopos", 16, 10, 14, 1, 1), ("gated", 16, 56, 4, 0, 1)])
+def test_ragged_lengths_match_oracle(variant, C, H, W, axis, stride):
+    """Lengths that are not powers of two / multiples of 4 (the reference's default kernel_size is 56) take the
+    generic one-row-per-thread kernels and the scalar staging paths."""
+    from oracle import axial_np
+    import fill
+    rs = np.random.RandomState(H * 100 + W)
+    N, L, gp = 2, (H if axis == 0 else W), C // 8
+    name = f"ragged.{variant}.{C}.{H}.{W}"
+    nsim, nout = (8, C) if variant == "nopos" else (24, 2 * C)
+    p = {"w_qkv": fill.tensor_for(name + ".qkv_transform.weight", (2 * C, C))}
+    for bn, short, n in (("bn_qkv", "bn_qkv", 2 * C), ("bn_similarity", "bn_sim", nsim), ("bn_output", "bn_out", nout)):
+        for leaf, suf in (("weight", "_w"), ("bias", "_b"), ("running_mean", "_rm"), ("running_var", "_rv")):
+            p[short + suf] = fill.tensor_for(f"{name}.{bn}.{leaf}", (n,))
+    if variant != "nopos":
+        p["relative"] = fill.tensor_for(name + ".relative", (2 * gp, 2 * L - 1))
+    if variant == "gated":
+        p["gates"] = (0.3, -0.2, 0.9, 0.15)
+    x = rs.standard_normal((N, C, H, W))
+    cfg = dict(C=C, N=N, H=H, W=W, axis=axis, stride=stride, ngroups=1, variant=variant, L=L)
+    for training in (True, False):
+        out_ref, cache, _ = axial_np.axial_forward(x, p, axis, stride, variant, training=training)
+        dout = rs.standard_normal(out_ref.shape)
+        gref = axial_np.axial_backward(dout, cache)
+        mod = build_module(cfg, p, name).train(training)
+        xt = torch.tensor(x, dtype=torch.float32, device="cuda", requires_grad=True)
+        out = mod(xt)
+        out.backward(torch.tensor(dout, dtype=torch.float32, device="cuda"))
+        assert rel_err(out.detach().cpu().numpy(), out_ref) < 1e-4
+        assert rel_err(xt.grad.cpu().numpy(), gref["dx"]) < 2e-3
+        assert rel_err(mod.qkv_transform.weight.grad.cpu().numpy()[:, :, 0], gref["dw_qkv"]) < 2e-3
+        if variant != "nopos":
+            assert rel_err(mod.relative.grad.cpu().numpy(), gref["drelative"]) < 2e-3
