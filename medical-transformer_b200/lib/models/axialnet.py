@@ -117,11 +117,41 @@ class _AxialBlockBase(nn.Module):
 
     def forward(self, x):
         g = self._stat_groups
+        idt, side, cur = x, None, None
+        if self.downsample is not None:
+            # the projection shortcut (1x1 conv + BN) is independent of the main branch until the residual add:
+            # fork it onto a second stream so it (and, through autograd, its backward) overlaps the attention chain
+            side = _fork_stream(x) if x.is_cuda else None
+            if side is not None:
+                cur = torch.cuda.current_stream(x.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    idt = bn_act(conv1x1_op(x, self.downsample[0]), self.downsample[1], g, relu=False)
+            else:
+                idt = bn_act(conv1x1_op(x, self.downsample[0]), self.downsample[1], g, relu=False)
         out = bn_act(conv1x1_op(x, self.conv_down), self.bn1, g, relu=True)
         out = self.width_block(self.hight_block(out))
-        if self.downsample is not None:
-            x = bn_act(conv1x1_op(x, self.downsample[0]), self.downsample[1], g, relu=False)
-        return bn_act(conv1x1_op(F.relu(out), self.conv_up), self.bn2, g, relu=True, residual=x)
+        out = conv1x1_op(F.relu(out), self.conv_up)
+        if side is not None:
+            cur.wait_stream(side)
+            idt.record_stream(cur)
+        return bn_act(out, self.bn2, g, relu=True, residual=idt)
+
+
+_FORK_STREAMS = {}
+
+
+def _fork_stream(x):
+    """One forked stream per (device, current stream): the shortcut branches of blocks running on different
+    streams (MedT's global / local branches) must not share one, or they would serialise each other."""
+    if os.environ.get("MEDT_NO_BRANCH_STREAM"):
+        return None
+    cur = torch.cuda.current_stream(x.device)
+    key = (x.device.index, cur.cuda_stream)
+    st = _FORK_STREAMS.get(key)
+    if st is None:
+        st = _FORK_STREAMS[key] = torch.cuda.Stream(device=x.device)
+    return st
 
 
 class AxialBlock(_AxialBlockBase):
