@@ -24,6 +24,9 @@
  *   - re-entrant: the device is whatever is current on the calling thread (torch's device
  *     guard), so nn.DataParallel's one-thread-per-GPU model works.
  *   - all tensors fp32, activations NCHW (the reference's layout and dtype).
+ *   - activation, `saved`, `workspace` and dx buffers and w_qkv must be dense and 16-byte aligned (128-bit
+ *     loads, TMA bulk copies); a misaligned pointer is MT_ERR_BAD_ARG, never a fault.  mt_bn_act_* instead
+ *     falls back to its scalar kernels; mt_conv1x1_* has no alignment requirement.
  */
 #ifndef MEDT_AXIAL_H_
 #define MEDT_AXIAL_H_

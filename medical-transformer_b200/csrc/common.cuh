@@ -32,6 +32,8 @@ struct Dims {
 };
 
 static inline size_t mt_align(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+// activation / scratch buffers are read with 128-bit loads and TMA bulk copies: the ABI requires 16-byte alignment
+static inline bool mt_al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static inline bool make_dims(const MtAxialDesc* d, Dims& m) {
   m.N = d->N; m.C = d->C; m.H = d->H; m.W = d->W; m.axis = d->axis; m.stride = d->stride;

@@ -74,6 +74,7 @@ static int check_common(const MtAxialDesc* d, const MtAxialParams* p, Dims& m) {
       !p->bn_sim_rm || !p->bn_sim_rv || !p->bn_out_w || !p->bn_out_b || !p->bn_out_rm || !p->bn_out_rv)
     return fail(MT_ERR_BAD_ARG, "null parameter pointer");
   if (m.pos && !p->relative) return fail(MT_ERR_BAD_ARG, "relative is required for the position variants");
+  if (!mt_al16(p->w_qkv)) return fail(MT_ERR_BAD_ARG, "w_qkv must be 16-byte aligned");
   return MT_OK;
 }
 
@@ -100,6 +101,7 @@ static int forward_impl(const MtAxialDesc* d, const MtAxialParams* p, const floa
   int rc = check_common(d, p, m);
   if (rc) return rc;
   if (!x || !out || !saved) return fail(MT_ERR_BAD_ARG, "null x / out / saved");
+  if (!mt_al16(x) || !mt_al16(out) || !mt_al16(saved)) return fail(MT_ERR_BAD_ARG, "x / out / saved must be 16-byte aligned");
   g_launches = 0;
   int r = axial_forward_launch(m, *p, x, out, static_cast<char*>(saved), static_cast<cudaStream_t>(stream), &g_launches, mask);
   if (r == -2) return fail(MT_ERR_UNSUPPORTED, "shape needs more shared memory than one CTA has (C*L too large)");
@@ -121,6 +123,8 @@ static int backward_impl(const MtAxialDesc* d, const MtAxialParams* p, const flo
   int rc = check_common(d, p, m);
   if (rc) return rc;
   if (!x || !dout || !saved || !workspace || !g) return fail(MT_ERR_BAD_ARG, "null x / dout / saved / workspace / grads");
+  if (!mt_al16(x) || !mt_al16(dout) || !mt_al16(saved) || !mt_al16(workspace) || !mt_al16(g->dx))
+    return fail(MT_ERR_BAD_ARG, "x / dout / saved / workspace / dx must be 16-byte aligned");
   g_launches = 0;
   int r = axial_backward_launch(m, *p, x, dout, static_cast<const char*>(saved), static_cast<char*>(workspace), *g,
                                 static_cast<cudaStream_t>(stream), &g_launches, mask);

@@ -322,6 +322,7 @@ extern "C" {
 int mt_up2x_relu_add_forward(int planes, int H, int W, const float* in, const float* skip, float* out,
                              unsigned char* mask, void* stream) {
   if (planes <= 0 || H <= 0 || W <= 0 || !in || !out) return mt_fail_msg(MT_ERR_BAD_ARG, "mt_up2x_relu_add_forward: bad argument");
+  if (!mt_al16(out) || !mt_al16(skip)) return mt_fail_msg(MT_ERR_BAD_ARG, "mt_up2x_relu_add_forward: out / skip must be 16-byte aligned");
   const long total = (long)planes * 2 * H * W;
   k_up2x_fwd<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(planes, H, W, in, skip, out, mask);
   g_last_cuda = cudaGetLastError();
@@ -346,9 +347,10 @@ int mt_bn_act_forward(int N, int C, int HW, int groups, int training, int relu, 
     return mt_fail_msg(MT_ERR_BAD_ARG, "mt_bn_act_forward: bad argument");
   if (training && (long)(N / groups) * HW < 2) return mt_fail_msg(MT_ERR_BAD_ARG, "mt_bn_act_forward: training needs more than one value per channel");
   BnActArgs a{N, C, HW, groups, training, relu, eps, momentum};
-  const int cnt = (N / groups) * HW / (HW % 4 == 0 ? 4 : 1);
+  const bool vec = HW % 4 == 0 && mt_al16(x) && mt_al16(y) && mt_al16(residual);   // else the scalar kernels
+  const int cnt = (N / groups) * HW / (vec ? 4 : 1);
   const int bs = cnt >= 1024 ? 256 : (cnt >= 256 ? 128 : 64);
-  if (HW % 4 == 0)
+  if (vec)
     k_bn_act_fwd<true><<<dim3(C, groups), bs, 0, (cudaStream_t)stream>>>(a, x, residual, gamma, beta, running_mean,
                                                                            running_var, y, save_mean, save_invstd);
   else
@@ -371,9 +373,10 @@ int mt_bn_act_backward(int N, int C, int HW, int groups, int training, int relu,
     cudaMemsetAsync(dgamma, 0, sizeof(float) * C, (cudaStream_t)stream);
     cudaMemsetAsync(dbeta, 0, sizeof(float) * C, (cudaStream_t)stream);
   }
-  const int cnt = (N / groups) * HW / (HW % 4 == 0 ? 4 : 1);
+  const bool vec = HW % 4 == 0 && mt_al16(x) && mt_al16(y) && mt_al16(dy) && mt_al16(dx) && mt_al16(dresidual);
+  const int cnt = (N / groups) * HW / (vec ? 4 : 1);
   const int bs = cnt >= 1024 ? 256 : (cnt >= 256 ? 128 : 64);
-  if (HW % 4 == 0)
+  if (vec)
     k_bn_act_bwd<true><<<dim3(C, groups), bs, 0, (cudaStream_t)stream>>>(a, x, y, dy, gamma, save_mean, save_invstd, dx,
                                                                            dresidual, dgamma, dbeta);
   else

@@ -5,6 +5,8 @@ header declares is exported and that sizeof() agrees."""
 from __future__ import annotations
 
 import ctypes as C
+
+import torch
 import os
 import threading
 
@@ -114,3 +116,14 @@ LAUNCHES = {"kernels": 0}
 
 def count_launches():
     LAUNCHES["kernels"] += int(load_library().mt_last_launch_count())
+
+
+def dense(t):
+    """Contiguous AND 16-byte aligned (the kernels use 128-bit loads and TMA bulk copies on activation buffers;
+    a contiguous view at an odd storage offset is copied)."""
+    if t is None:
+        return None
+    t = t.contiguous()
+    if t.data_ptr() & 15:
+        t = t.clone(memory_format=torch.contiguous_format)
+    return t

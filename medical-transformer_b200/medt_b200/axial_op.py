@@ -43,7 +43,7 @@ class AxialAttnFunction(torch.autograd.Function):
                 q_rm, q_rv, s_rm, s_rv, o_rm, o_rv, cfg):
         axis, stride, variant, training, ngroups, eps, momentum = cfg
         lib = _cabi.load_library()
-        x = x.contiguous()
+        x = _cabi.dense(x)
         for name, t in (("x", x), ("qkv_transform.weight", w_qkv), ("relative", relative), ("f_qr", f_qr),
                         ("bn_qkv.weight", q_w), ("bn_similarity.weight", s_w), ("bn_output.weight", o_w),
                         ("bn_qkv.running_mean", q_rm), ("bn_similarity.running_var", s_rv)):
@@ -76,7 +76,7 @@ class AxialAttnFunction(torch.autograd.Function):
          q_rm, q_rv, s_rm, s_rv, o_rm, o_rv, saved) = ctx.saved_tensors
         axis, stride, variant, training, ngroups, eps, momentum = ctx.cfg
         lib = _cabi.load_library()
-        dout = dout.contiguous()
+        dout = _cabi.dense(dout)
         _check_tensor(dout, "grad_output")
         desc = _desc(x, axis, stride, variant, training, ngroups, eps, momentum)
         params = _cabi.MtAxialParams(_ptr(w_qkv), _ptr(relative), _ptr(f_qr), _ptr(f_kr), _ptr(f_sv), _ptr(f_sve),

@@ -32,9 +32,9 @@ class Up2xReluAdd(torch.autograd.Function):
     def forward(ctx, x, skip):
         _need_cuda(x, "up2x_relu_add")
         lib = _cabi.load_library()
-        x = x.contiguous()
+        x = _cabi.dense(x)
         n, c, h, w = x.shape
-        skip_c = None if skip is None else skip.contiguous()
+        skip_c = None if skip is None else _cabi.dense(skip)
         out = torch.empty((n, c, 2 * h, 2 * w), dtype=torch.float32, device=x.device)
         need_bwd = x.requires_grad or (skip is not None and skip.requires_grad)
         mask = torch.empty((n, c, 2 * h, 2 * w), dtype=torch.uint8, device=x.device) if need_bwd else None
@@ -52,7 +52,7 @@ class Up2xReluAdd(torch.autograd.Function):
         (mask,) = ctx.saved_tensors
         n, c, h, w = ctx.shape
         lib = _cabi.load_library()
-        dout = dout.contiguous()
+        dout = _cabi.dense(dout)
         din = None
         if ctx.needs_input_grad[0]:
             din = torch.empty((n, c, h, w), dtype=torch.float32, device=dout.device)
@@ -73,8 +73,8 @@ class BnAct(torch.autograd.Function):
         groups, training, relu, eps, momentum = cfg
         _need_cuda(x, "bn_act")
         lib = _cabi.load_library()
-        x = x.contiguous()
-        res = None if residual is None else residual.contiguous()
+        x = _cabi.dense(x)
+        res = None if residual is None else _cabi.dense(residual)
         n, c, h, w = x.shape
         y = torch.empty_like(x)
         save_mean = torch.empty((2 * groups, c), dtype=torch.float32, device=x.device)
@@ -95,7 +95,7 @@ class BnAct(torch.autograd.Function):
         x, y, weight, save_mean, save_invstd = ctx.saved_tensors
         groups, training, relu, eps, momentum = ctx.cfg
         lib = _cabi.load_library()
-        dy = dy.contiguous()
+        dy = _cabi.dense(dy)
         n, c, h, w = x.shape
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if (ctx.has_res and ctx.needs_input_grad[1]) else None
@@ -131,7 +131,7 @@ class Conv1x1(torch.autograd.Function):
     def forward(ctx, x, weight, stride):
         _need_cuda(x, "conv1x1")
         lib = _cabi.load_library()
-        x = x.contiguous()
+        x = _cabi.dense(x)
         n, ci, h, w = x.shape
         co = weight.shape[0]
         ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
@@ -148,7 +148,7 @@ class Conv1x1(torch.autograd.Function):
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
         lib = _cabi.load_library()
-        dy = dy.contiguous()
+        dy = _cabi.dense(dy)
         n, ci, h, w = x.shape
         co = weight.shape[0]
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None

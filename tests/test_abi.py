@@ -69,6 +69,40 @@ def test_size_queries_and_argument_errors():
     assert rc == 2
 
 
+def test_misaligned_buffers_are_rejected_before_any_launch():
+    """Activation buffers are read with 128-bit loads / TMA bulk copies: the ABI refuses pointers that are not
+    16-byte aligned (argument check only -- nothing is dereferenced or launched)."""
+    from medt_b200 import _cabi
+    lib = _cabi.load_library()
+    d = _cabi.MtAxialDesc(1, 16, 8, 8, 0, 1, 2, 0, 1, 1e-5, 0.1)           # nopos, eval
+    p = _cabi.MtAxialParams()
+    fake = ctypes.c_void_p(0x1000)
+    for name, _ in _cabi.MtAxialParams._fields_:
+        setattr(p, name, fake)
+    ok, off = ctypes.c_void_p(0x2000), ctypes.c_void_p(0x2004)
+    rc = lib.mt_axial_forward(ctypes.byref(d), ctypes.byref(p), off, ok, ok, None)
+    assert rc == 1 and b"16-byte aligned" in lib.mt_last_error()
+    rc = lib.mt_axial_forward(ctypes.byref(d), ctypes.byref(p), ok, ok, off, None)
+    assert rc == 1 and b"16-byte aligned" in lib.mt_last_error()
+    p.w_qkv = ctypes.c_void_p(0x1008)
+    rc = lib.mt_axial_forward(ctypes.byref(d), ctypes.byref(p), ok, ok, ok, None)
+    assert rc == 1 and b"w_qkv" in lib.mt_last_error()
+    rc = lib.mt_up2x_relu_add_forward(1, 4, 4, ok, off, ok, ok, None)
+    assert rc == 1 and b"aligned" in lib.mt_last_error()
+
+
+def test_dense_returns_contiguous_aligned_tensors():
+    import torch
+    from medt_b200 import _cabi
+    base = torch.arange(4 * 9, dtype=torch.float32)
+    view = base[1:33].view(2, 16)                                          # contiguous, storage offset 4 bytes
+    assert view.is_contiguous() and view.data_ptr() % 16 != 0
+    t = _cabi.dense(view)
+    assert t.data_ptr() % 16 == 0 and t.is_contiguous() and torch.equal(t, view)
+    assert _cabi.dense(base) is base and _cabi.dense(None) is None
+    assert _cabi.dense(base.view(6, 6).t()).is_contiguous()
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     from medt_b200 import _cabi
     monkeypatch.setattr(_cabi, "_LIB", None)

@@ -81,3 +81,21 @@ def test_shell_ops_refuse_cpu():
     from medt_b200.shell_ops import up2x_relu_add
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         up2x_relu_add(torch.randn(1, 1, 2, 2))
+
+
+def test_misaligned_contiguous_views_give_the_same_result():
+    """A contiguous view at an odd storage offset (4-byte aligned only) goes through `_cabi.dense()`; the raw ABI
+    refuses it (tests/test_abi.py) instead of faulting in a 128-bit load."""
+    import lib
+    from medt_b200.shell_ops import bn_act, up2x_relu_add
+    torch.manual_seed(5)
+    n, c, h, w = 2, 16, 8, 8
+    base = torch.randn(n * c * h * w + 1, device="cuda")
+    xv = base[1:].view(n, c, h, w)
+    assert xv.is_contiguous() and xv.data_ptr() % 16 != 0
+    xa = xv.clone()
+    mod = lib.models.axialnet.AxialAttention_dynamic(c, c, groups=8, kernel_size=h).cuda()
+    bn = torch.nn.BatchNorm2d(c).cuda()
+    for fn in (lambda t: mod(t), lambda t: bn_act(t, bn, 1, relu=True), lambda t: up2x_relu_add(t, None)):
+        a, b = fn(xa), fn(xv)
+        assert torch.equal(a, b)
