@@ -98,4 +98,5 @@ def test_misaligned_contiguous_views_give_the_same_result():
     bn = torch.nn.BatchNorm2d(c).cuda()
     for fn in (lambda t: mod(t), lambda t: bn_act(t, bn, 1, relu=True), lambda t: up2x_relu_add(t, None)):
         a, b = fn(xa), fn(xv)
-        assert torch.equal(a, b)
+        # same kernels, same data: only the order of the fp64 statistic atomics differs between two launches
+        assert (a - b).abs().max().item() <= 1e-5 * a.abs().max().item()
