@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define MT_ABI_VERSION 1
+#define MT_ABI_VERSION 2
 
 enum MtStatus {
   MT_OK = 0,
@@ -113,12 +113,16 @@ int mt_axial_backward(const MtAxialDesc* d, const MtAxialParams* p, const float*
  * relu(F.interpolate(in, scale_factor=2, mode='bilinear', align_corners=False)) + skip
  *   <- one decoder step, axialnet.py:493-501 / :650-652 / :690-698.
  * in: (planes, H, W) with planes = N*C; out / skip / mask: (planes, 2H, 2W); skip may be NULL;
- * mask (1 byte per output, = pre-activation > 0) may be NULL when no backward will follow. */
-int mt_up2x_relu_add_forward(int planes, int H, int W, const float* in, const float* skip, float* out,
-                             unsigned char* mask, void* stream);
-/* din = upsample^T(dout * mask); the gradient of `skip` is dout itself (not written). */
-int mt_up2x_relu_add_backward(int planes, int H, int W, const float* dout, const unsigned char* mask, float* din,
-                              void* stream);
+ * mask (1 byte per output, = pre-activation > 0) may be NULL when no backward will follow.
+ * bias (C floats, nullable): the bias of the decoder conv that produced `in`, added here instead of by a separate
+ * elementwise pass -- relu(up(in + b)) == relu(up(in) + b) because the bilinear taps sum to 1. */
+int mt_up2x_relu_add_forward(int planes, int C, int H, int W, const float* in, const float* bias, const float* skip,
+                             float* out, unsigned char* mask, void* stream);
+/* din = upsample^T(dout * mask); the gradient of `skip` is dout itself (not written).
+ * dbias (C floats, nullable, overwritten) = sum over (n, h, w) of din: the conv's bias gradient, reduced in the same
+ * pass (fp32 atomics: last-bit run-to-run differences). */
+int mt_up2x_relu_add_backward(int planes, int C, int H, int W, const float* dout, const unsigned char* mask, float* din,
+                              float* dbias, void* stream);
 
 /* y = [relu]( BatchNorm2d(x) [+ residual] ) with batch statistics per statistic group
  *   <- bn+relu(+identity) of AxialBlock*.forward axialnet.py:285-300 / :327-342 / :373-389, the
@@ -137,10 +141,12 @@ int mt_bn_act_backward(int N, int C, int HW, int groups, int training, int relu,
 
 /* Bias-free 1x1 convolution (conv_down / conv_up / downsample of the blocks: `conv1x1`, axialnet.py:14-16,
  * :272-276, :450-453) as a tiled fp32 SGEMM.  x: (N,Ci,H,W), w: (Co,Ci), y / dy: (N,Co,Ho,Wo) with
- * Ho = (H-1)/stride+1.  backward overwrites dx (N,Ci,H,W) and dw (Co,Ci); either may be NULL. */
-int mt_conv1x1_forward(int N, int Ci, int Co, int H, int W, int stride, const float* x, const float* w, float* y,
-                       void* stream);
-int mt_conv1x1_backward(int N, int Ci, int Co, int H, int W, int stride, const float* x, const float* w,
+ * Ho = (H-1)/stride+1.  backward overwrites dx (N,Ci,H,W) and dw (Co,Ci); either may be NULL.
+ * relu_in != 0: the conv reads relu(x) (`conv_up(self.relu(output))`, axialnet.py:291-293 / :333-335 / :380-382) -- the ReLU is
+ * applied while loading the operand and its backward while storing dx; pass the SAME (pre-ReLU) x to backward. */
+int mt_conv1x1_forward(int N, int Ci, int Co, int H, int W, int stride, int relu_in, const float* x, const float* w,
+                       float* y, void* stream);
+int mt_conv1x1_backward(int N, int Ci, int Co, int H, int W, int stride, int relu_in, const float* x, const float* w,
                         const float* dy, float* dx, float* dw, void* stream);
 
 /* Profiling hooks (bench.py roofline, ncu): launch only the stages selected by `stage_mask`

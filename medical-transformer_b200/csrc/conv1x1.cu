@@ -4,6 +4,7 @@
 //   k_c1_fwd   Y[n][co][q] = sum_ci W[co][ci] X[n][ci][src(q)]
 //   k_c1_dx    dX[n][ci][src(q)] = sum_co W[co][ci] dY[n][co][q]          (other dX entries stay zero)
 //   k_c1_dw    dW[co][ci] += sum_{n,q} dY[n][co][q] X[n][ci][src(q)]       (split over position chunks)
+// relu_in = 1 folds the ReLU in front of conv_up (axialnet.py:291-293, :333-335, :380-382) into the operand loads / the dX store.
 // cuDNN's fp32 (non-TF32) kernels for these shapes take 17-29 us each (profiles/r1_notes.md); TF32 is not
 // an option.
 #include "common.cuh"
@@ -13,7 +14,7 @@ cudaStream_t mt_side_fork(cudaStream_t main_stream);
 void mt_side_join(cudaStream_t main_stream, cudaStream_t forked);
 
 #define C1_LD 68
-struct C1Args { int N, Ci, Co, H, W, stride, Ho, Wo; };
+struct C1Args { int N, Ci, Co, H, W, stride, Ho, Wo, relu_in; };   // relu_in: the conv reads relu(x) (conv_up of the blocks)
 
 __device__ __forceinline__ void c1_mma(const float* As, const float* Bs, int ty, int tx, float acc[4][4]) {
 #pragma unroll
@@ -65,6 +66,7 @@ k_c1_fwd(C1Args a, const float* __restrict__ x, const float* __restrict__ w, flo
       va[it] = (co0 + mm < a.Co && k0 + kk < a.Ci) ? __ldg(w + (size_t)(co0 + mm) * a.Ci + k0 + kk) : 0.f;
       const int kb = (tid >> 6) + 4 * it;           // B: X[k0+kb][pos], pos = tid & 63
       vb[it] = (pok && k0 + kb < a.Ci) ? __ldg(xb + (size_t)(k0 + kb) * HW) : 0.f;
+      if (a.relu_in) vb[it] = fmaxf(vb[it], 0.f);
     }
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
@@ -89,7 +91,8 @@ k_c1_fwd(C1Args a, const float* __restrict__ x, const float* __restrict__ w, flo
 
 // grid (ceil(P/64), ceil(Ci/64)); M = ci, N = positions, K = co
 __global__ void __launch_bounds__(256)
-k_c1_dx(C1Args a, const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx) {
+k_c1_dx(C1Args a, const float* __restrict__ dy, const float* __restrict__ w, const float* __restrict__ x,
+        float* __restrict__ dx) {
   __shared__ __align__(16) float As[16 * C1_LD], Bs[16 * C1_LD];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int ci0 = blockIdx.y * 64;
@@ -127,7 +130,10 @@ k_c1_dx(C1Args a, const float* __restrict__ dy, const float* __restrict__ w, flo
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int ci = ci0 + ty * 4 + i;
-      if (ci < a.Ci) dx[((size_t)n * a.Ci + ci) * HW + src] = acc[i][j];
+      if (ci < a.Ci) {
+        const size_t o = ((size_t)n * a.Ci + ci) * HW + src;
+        dx[o] = (a.relu_in && !(__ldg(x + o) > 0.f)) ? 0.f : acc[i][j];      // d relu: the gradient passes where x > 0
+      }
     }
   }
 }
@@ -159,6 +165,7 @@ k_c1_dw(C1Args a, const float* __restrict__ dy, const float* __restrict__ x, flo
         const int mm = m0 + 4 * u;
         vy[u] = (pok && co0 + mm < a.Co) ? __ldg(yb + (size_t)(co0 + mm) * HWo) : 0.f;
         vx[u] = (pok && ci0 + mm < a.Ci) ? __ldg(xb + (size_t)(ci0 + mm) * HW) : 0.f;
+        if (a.relu_in) vx[u] = fmaxf(vx[u], 0.f);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) { Am[r * C1_LD + m0 + 4 * u] = vy[u]; Bm[r * C1_LD + m0 + 4 * u] = vx[u]; }
@@ -179,22 +186,22 @@ k_c1_dw(C1Args a, const float* __restrict__ dy, const float* __restrict__ x, flo
 
 extern "C" {
 
-int mt_conv1x1_forward(int N, int Ci, int Co, int H, int W, int stride, const float* x, const float* w, float* y,
-                       void* stream) {
+int mt_conv1x1_forward(int N, int Ci, int Co, int H, int W, int stride, int relu_in, const float* x, const float* w,
+                       float* y, void* stream) {
   if (N <= 0 || Ci <= 0 || Co <= 0 || H <= 0 || W <= 0 || stride < 1 || !x || !w || !y)
     return mt_fail_msg(MT_ERR_BAD_ARG, "mt_conv1x1_forward: bad argument");
-  C1Args a{N, Ci, Co, H, W, stride, (H - 1) / stride + 1, (W - 1) / stride + 1};
+  C1Args a{N, Ci, Co, H, W, stride, (H - 1) / stride + 1, (W - 1) / stride + 1, relu_in ? 1 : 0};
   const long P = (long)N * a.Ho * a.Wo;
   k_c1_fwd<<<dim3((unsigned)((P + 63) / 64), (Co + 63) / 64), 256, 0, (cudaStream_t)stream>>>(a, x, w, y);
   g_last_cuda = cudaGetLastError();
   return g_last_cuda == cudaSuccess ? MT_OK : mt_fail_msg(MT_ERR_CUDA, "mt_conv1x1_forward: launch failed");
 }
 
-int mt_conv1x1_backward(int N, int Ci, int Co, int H, int W, int stride, const float* x, const float* w, const float* dy,
-                        float* dx, float* dw, void* stream) {
+int mt_conv1x1_backward(int N, int Ci, int Co, int H, int W, int stride, int relu_in, const float* x, const float* w,
+                        const float* dy, float* dx, float* dw, void* stream) {
   if (N <= 0 || Ci <= 0 || Co <= 0 || H <= 0 || W <= 0 || stride < 1 || !x || !w || !dy)
     return mt_fail_msg(MT_ERR_BAD_ARG, "mt_conv1x1_backward: bad argument");
-  C1Args a{N, Ci, Co, H, W, stride, (H - 1) / stride + 1, (W - 1) / stride + 1};
+  C1Args a{N, Ci, Co, H, W, stride, (H - 1) / stride + 1, (W - 1) / stride + 1, relu_in ? 1 : 0};
   const long P = (long)N * a.Ho * a.Wo;
   cudaStream_t st = (cudaStream_t)stream;
   cudaStream_t sd = (dw && dx) ? mt_side_fork(st) : st;          // dW next to dX, not behind it
@@ -210,7 +217,7 @@ int mt_conv1x1_backward(int N, int Ci, int Co, int H, int W, int stride, const f
   }
   if (dx) {
     if (stride > 1) cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)N * Ci * H * W, st);
-    k_c1_dx<<<dim3((unsigned)((P + 63) / 64), (Ci + 63) / 64), 256, 0, st>>>(a, dy, w, dx);
+    k_c1_dx<<<dim3((unsigned)((P + 63) / 64), (Ci + 63) / 64), 256, 0, st>>>(a, dy, w, x, dx);
   }
   mt_side_join(st, sd);
   g_last_cuda = cudaGetLastError();

@@ -23,8 +23,8 @@ __device__ __forceinline__ void up_taps(int dst, int n_in, int& i0, int& i1, flo
 
 // one thread per output pixel pair along W (float2 store); mask byte = (pre-activation > 0)
 __global__ void __launch_bounds__(256)
-k_up2x_fwd(int planes, int H, int W, const float* __restrict__ in, const float* __restrict__ skip,
-           float* __restrict__ out, unsigned char* __restrict__ mask) {
+k_up2x_fwd(int planes, int C, int H, int W, const float* __restrict__ in, const float* __restrict__ bias,
+           const float* __restrict__ skip, float* __restrict__ out, unsigned char* __restrict__ mask) {
   const int Wo = 2 * W, Ho = 2 * H;
   const long total = (long)planes * Ho * W;                 // W pairs per output row
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -44,6 +44,10 @@ k_up2x_fwd(int planes, int H, int W, const float* __restrict__ in, const float* 
   const float a_p = (1.f - lh) * __ldg(r0 + wpl) + lh * __ldg(r1 + wpl);
   float v0 = wp > 0 ? 0.25f * a_m + 0.75f * a_c : a_c;
   float v1 = 0.75f * a_c + 0.25f * a_p;                     // at wp == W-1: a_p == a_c -> a_c
+  if (bias) {                                               // the taps sum to 1: conv bias commutes with the upsample
+    const float bb = __ldg(bias + (int)(pl % C));
+    v0 += bb; v1 += bb;
+  }
   const long o = (pl * Ho + ho) * Wo + 2 * wp;
   unsigned char m0 = v0 > 0.f, m1 = v1 > 0.f;
   v0 = m0 ? v0 : 0.f; v1 = m1 ? v1 : 0.f;
@@ -52,13 +56,15 @@ k_up2x_fwd(int planes, int H, int W, const float* __restrict__ in, const float* 
   if (mask) { mask[o] = m0; mask[o + 1] = m1; }
 }
 
-// gather form: one thread per input pixel sums its (up to) 4x4 masked output gradients
+// gather form: one thread per input pixel sums its (up to) 4x4 masked output gradients; with `dbias` the same
+// pass also reduces d bias[c] = sum over (n, h, w) of din (warp shuffle -> CTA -> one atomic per channel run)
 __global__ void __launch_bounds__(256)
-k_up2x_bwd(int planes, int H, int W, const float* __restrict__ dout, const unsigned char* __restrict__ mask,
-           float* __restrict__ din) {
+k_up2x_bwd(int planes, int C, int H, int W, const float* __restrict__ dout, const unsigned char* __restrict__ mask,
+           float* __restrict__ din, float* __restrict__ dbias) {
   const long total = (long)planes * H * W;
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
+  const long gidx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool act = gidx < total;
+  const long idx = act ? gidx : total - 1;
   const int w = (int)(idx % W);
   const long t = idx / W;
   const int h = (int)(t % H);
@@ -89,7 +95,32 @@ k_up2x_bwd(int planes, int H, int W, const float* __restrict__ dout, const unsig
     }
     acc = fmaf(wr[a], rowacc, acc);
   }
-  din[idx] = acc;
+  if (act) din[idx] = acc;
+  if (!dbias) return;                                       // uniform over the grid
+  __shared__ float wsum[8];
+  __shared__ int wch[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int ch = act ? (int)(pl % C) : -1;
+  const int ch0 = __shfl_sync(0xffffffffu, ch, 0);
+  const bool uni = __all_sync(0xffffffffu, ch == ch0);      // whole warp inside one channel plane (the usual case)
+  float sacc = uni ? acc : 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+  if (!uni && act) atomicAdd(dbias + ch, acc);
+  if (lane == 0) { wsum[wid] = sacc; wch[wid] = uni ? ch0 : -1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nw = blockDim.x >> 5;
+    int cur = -1; float run = 0.f;                          // merge runs of warps that share a channel
+    for (int k = 0; k < nw; ++k) {
+      if (wch[k] != cur) {
+        if (cur >= 0) atomicAdd(dbias + cur, run);
+        cur = wch[k]; run = 0.f;
+      }
+      run += wsum[k];
+    }
+    if (cur >= 0) atomicAdd(dbias + cur, run);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -319,21 +350,24 @@ int mt_fail_msg(int code, const char* msg);
 
 extern "C" {
 
-int mt_up2x_relu_add_forward(int planes, int H, int W, const float* in, const float* skip, float* out,
-                             unsigned char* mask, void* stream) {
-  if (planes <= 0 || H <= 0 || W <= 0 || !in || !out) return mt_fail_msg(MT_ERR_BAD_ARG, "mt_up2x_relu_add_forward: bad argument");
+int mt_up2x_relu_add_forward(int planes, int C, int H, int W, const float* in, const float* bias, const float* skip,
+                             float* out, unsigned char* mask, void* stream) {
+  if (planes <= 0 || C <= 0 || planes % C || H <= 0 || W <= 0 || !in || !out)
+    return mt_fail_msg(MT_ERR_BAD_ARG, "mt_up2x_relu_add_forward: bad argument");
   if (!mt_al16(out) || !mt_al16(skip)) return mt_fail_msg(MT_ERR_BAD_ARG, "mt_up2x_relu_add_forward: out / skip must be 16-byte aligned");
   const long total = (long)planes * 2 * H * W;
-  k_up2x_fwd<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(planes, H, W, in, skip, out, mask);
+  k_up2x_fwd<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(planes, C, H, W, in, bias, skip, out, mask);
   g_last_cuda = cudaGetLastError();
   return g_last_cuda == cudaSuccess ? MT_OK : mt_fail_msg(MT_ERR_CUDA, "mt_up2x_relu_add_forward: launch failed");
 }
 
-int mt_up2x_relu_add_backward(int planes, int H, int W, const float* dout, const unsigned char* mask, float* din,
-                              void* stream) {
-  if (planes <= 0 || H <= 0 || W <= 0 || !dout || !mask || !din) return mt_fail_msg(MT_ERR_BAD_ARG, "mt_up2x_relu_add_backward: bad argument");
+int mt_up2x_relu_add_backward(int planes, int C, int H, int W, const float* dout, const unsigned char* mask, float* din,
+                              float* dbias, void* stream) {
+  if (planes <= 0 || C <= 0 || planes % C || H <= 0 || W <= 0 || !dout || !mask || !din)
+    return mt_fail_msg(MT_ERR_BAD_ARG, "mt_up2x_relu_add_backward: bad argument");
   const long total = (long)planes * H * W;
-  k_up2x_bwd<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(planes, H, W, dout, mask, din);
+  if (dbias) cudaMemsetAsync(dbias, 0, sizeof(float) * C, (cudaStream_t)stream);
+  k_up2x_bwd<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(planes, C, H, W, dout, mask, din, dbias);
   g_last_cuda = cudaGetLastError();
   return g_last_cuda == cudaSuccess ? MT_OK : mt_fail_msg(MT_ERR_CUDA, "mt_up2x_relu_add_backward: launch failed");
 }

@@ -131,7 +131,10 @@ class _AxialBlockBase(nn.Module):
                 idt = bn_act(conv1x1_op(x, self.downsample[0]), self.downsample[1], g, relu=False)
         out = bn_act(conv1x1_op(x, self.conv_down), self.bn1, g, relu=True)
         out = self.width_block(self.hight_block(out))
-        out = conv1x1_op(F.relu(out), self.conv_up)
+        if os.environ.get("MEDT_NO_SHELL_FUSION"):
+            out = conv1x1_op(F.relu(out), self.conv_up)
+        else:
+            out = conv1x1_op(out, self.conv_up, relu_in=True)
         if side is not None:
             cur.wait_stream(side)
             idt.record_stream(cur)
@@ -170,7 +173,11 @@ class AxialBlock_wopos(_AxialBlockBase):
 # ----------------------------------------------------------------------------- shells
 def _up_relu(conv, x, skip=None):
     """relu(bilinear x2 (conv(x))) [+ skip] -- one decoder step (reference :493-501), one fused kernel."""
-    return up2x_relu_add(conv(x), skip)
+    if conv.bias is None or os.environ.get("MEDT_NO_SHELL_FUSION"):
+        return up2x_relu_add(conv(x), skip)
+    # the conv runs without its bias; the fused kernel adds it (the bilinear taps sum to 1) and reduces its gradient
+    y = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+    return up2x_relu_add(y, skip, conv.bias)
 
 
 class _ShellBase(nn.Module):

@@ -40,6 +40,8 @@ class MtAxialGrads(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in _GRAD_FIELDS]
 
 
+ABI_VERSION = 2        # == MT_ABI_VERSION of include/medt_axial.h
+
 EXPORTS = ["mt_version", "mt_last_error", "mt_last_launch_count", "mt_axial_saved_bytes",
            "mt_axial_bwd_workspace_bytes", "mt_axial_forward", "mt_axial_backward",
            "mt_axial_forward_stages", "mt_axial_backward_stages",
@@ -66,6 +68,9 @@ def load_library():
                 "(or `make -C medical-transformer_b200/csrc`). There is no CPU / eager fallback.")
         lib = C.CDLL(path)
         lib.mt_version.restype = C.c_int
+        if int(lib.mt_version()) != ABI_VERSION:
+            raise RuntimeError(f"medt_b200: {path} has ABI version {int(lib.mt_version())}, this host code binds "
+                               f"version {ABI_VERSION} (include/medt_axial.h) -- rebuild the library")
         lib.mt_last_error.restype = C.c_char_p
         lib.mt_last_launch_count.restype = C.c_int
         lib.mt_axial_saved_bytes.restype = C.c_size_t
@@ -84,17 +89,17 @@ def load_library():
         lib.mt_axial_backward_stages.argtypes = lib.mt_axial_backward.argtypes + [C.c_int]
         VP, I, F_ = C.c_void_p, C.c_int, C.c_float
         lib.mt_up2x_relu_add_forward.restype = C.c_int
-        lib.mt_up2x_relu_add_forward.argtypes = [I, I, I, VP, VP, VP, VP, VP]
+        lib.mt_up2x_relu_add_forward.argtypes = [I, I, I, I, VP, VP, VP, VP, VP, VP]
         lib.mt_up2x_relu_add_backward.restype = C.c_int
-        lib.mt_up2x_relu_add_backward.argtypes = [I, I, I, VP, VP, VP, VP]
+        lib.mt_up2x_relu_add_backward.argtypes = [I, I, I, I, VP, VP, VP, VP, VP]
         lib.mt_bn_act_forward.restype = C.c_int
         lib.mt_bn_act_forward.argtypes = [I, I, I, I, I, I, F_, F_, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP]
         lib.mt_bn_act_backward.restype = C.c_int
         lib.mt_bn_act_backward.argtypes = [I, I, I, I, I, I, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP]
         lib.mt_conv1x1_forward.restype = C.c_int
-        lib.mt_conv1x1_forward.argtypes = [I, I, I, I, I, I, VP, VP, VP, VP]
+        lib.mt_conv1x1_forward.argtypes = [I, I, I, I, I, I, I, VP, VP, VP, VP]
         lib.mt_conv1x1_backward.restype = C.c_int
-        lib.mt_conv1x1_backward.argtypes = [I, I, I, I, I, I, VP, VP, VP, VP, VP, VP]
+        lib.mt_conv1x1_backward.argtypes = [I, I, I, I, I, I, I, VP, VP, VP, VP, VP, VP]
         _LIB = lib
         return lib
 

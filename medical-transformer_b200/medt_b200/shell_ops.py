@@ -8,6 +8,7 @@ from __future__ import annotations
 import ctypes as C
 
 import torch
+import torch.nn.functional as F
 
 from . import _cabi
 
@@ -29,22 +30,25 @@ def _need_cuda(t, what):
 
 class Up2xReluAdd(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, skip):
+    def forward(ctx, x, skip, bias):
         _need_cuda(x, "up2x_relu_add")
         lib = _cabi.load_library()
         x = _cabi.dense(x)
         n, c, h, w = x.shape
         skip_c = None if skip is None else _cabi.dense(skip)
+        bias_c = None if bias is None else _cabi.dense(bias)
         out = torch.empty((n, c, 2 * h, 2 * w), dtype=torch.float32, device=x.device)
-        need_bwd = x.requires_grad or (skip is not None and skip.requires_grad)
+        need_bwd = x.requires_grad or (skip is not None and skip.requires_grad) or (bias is not None and bias.requires_grad)
         mask = torch.empty((n, c, 2 * h, 2 * w), dtype=torch.uint8, device=x.device) if need_bwd else None
         with torch.cuda.device(x.device):
-            rc = lib.mt_up2x_relu_add_forward(n * c, h, w, _p(x), _p(skip_c), _p(out), _p(mask), _stream(x.device))
+            rc = lib.mt_up2x_relu_add_forward(n * c, c, h, w, _p(x), _p(bias_c), _p(skip_c), _p(out), _p(mask),
+                                              _stream(x.device))
         _cabi.check(rc, "mt_up2x_relu_add_forward")
         _cabi.LAUNCHES["kernels"] += 1
         ctx.save_for_backward(mask)
         ctx.shape = (n, c, h, w)
         ctx.has_skip = skip is not None
+        ctx.has_bias = bias is not None
         return out
 
     @staticmethod
@@ -53,18 +57,24 @@ class Up2xReluAdd(torch.autograd.Function):
         n, c, h, w = ctx.shape
         lib = _cabi.load_library()
         dout = _cabi.dense(dout)
-        din = None
-        if ctx.needs_input_grad[0]:
+        din = dbias = None
+        want_bias = ctx.has_bias and ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[0] or want_bias:
             din = torch.empty((n, c, h, w), dtype=torch.float32, device=dout.device)
+            dbias = torch.empty((c,), dtype=torch.float32, device=dout.device) if want_bias else None
             with torch.cuda.device(dout.device):
-                rc = lib.mt_up2x_relu_add_backward(n * c, h, w, _p(dout), _p(mask), _p(din), _stream(dout.device))
+                rc = lib.mt_up2x_relu_add_backward(n * c, c, h, w, _p(dout), _p(mask), _p(din), _p(dbias),
+                                                   _stream(dout.device))
             _cabi.check(rc, "mt_up2x_relu_add_backward")
             _cabi.LAUNCHES["kernels"] += 1
-        return din, (dout if (ctx.has_skip and ctx.needs_input_grad[1]) else None)
+        return (din if ctx.needs_input_grad[0] else None,
+                dout if (ctx.has_skip and ctx.needs_input_grad[1]) else None, dbias)
 
 
-def up2x_relu_add(x, skip=None):
-    return Up2xReluAdd.apply(x, skip)
+def up2x_relu_add(x, skip=None, bias=None):
+    """relu(bilinear_x2(x + bias[None, :, None, None])) [+ skip]; `bias` is the producing conv's bias when the conv
+    itself was run without it (one elementwise pass and one reduction fewer per decoder step)."""
+    return Up2xReluAdd.apply(x, skip, bias)
 
 
 class BnAct(torch.autograd.Function):
@@ -128,7 +138,7 @@ def bn_act(x, bn, groups: int = 1, relu: bool = True, residual=None):
 
 class Conv1x1(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, stride):
+    def forward(ctx, x, weight, stride, relu_in):
         _need_cuda(x, "conv1x1")
         lib = _cabi.load_library()
         x = _cabi.dense(x)
@@ -137,11 +147,12 @@ class Conv1x1(torch.autograd.Function):
         ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
         y = torch.empty((n, co, ho, wo), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
-            rc = lib.mt_conv1x1_forward(n, ci, co, h, w, stride, _p(x), _p(weight), _p(y), _stream(x.device))
+            rc = lib.mt_conv1x1_forward(n, ci, co, h, w, stride, int(relu_in), _p(x), _p(weight), _p(y),
+                                        _stream(x.device))
         _cabi.check(rc, "mt_conv1x1_forward")
         _cabi.LAUNCHES["kernels"] += 1
         ctx.save_for_backward(x, weight)
-        ctx.stride = stride
+        ctx.stride, ctx.relu_in = stride, int(relu_in)
         return y
 
     @staticmethod
@@ -154,15 +165,16 @@ class Conv1x1(torch.autograd.Function):
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         dw = torch.empty_like(weight) if ctx.needs_input_grad[1] else None
         with torch.cuda.device(x.device):
-            rc = lib.mt_conv1x1_backward(n, ci, co, h, w, ctx.stride, _p(x), _p(weight), _p(dy), _p(dx), _p(dw),
-                                         _stream(x.device))
+            rc = lib.mt_conv1x1_backward(n, ci, co, h, w, ctx.stride, ctx.relu_in, _p(x), _p(weight), _p(dy), _p(dx),
+                                         _p(dw), _stream(x.device))
         _cabi.check(rc, "mt_conv1x1_backward")
         _cabi.LAUNCHES["kernels"] += (1 if dx is not None else 0) + (1 if dw is not None else 0)
-        return dx, dw, None
+        return dx, dw, None, None
 
 
-def conv1x1(x, conv):
-    """`conv` is the module's own bias-free nn.Conv2d(kernel_size=1) (weight (Co,Ci,1,1) used in place)."""
+def conv1x1(x, conv, relu_in=False):
+    """`conv` is the module's own bias-free nn.Conv2d(kernel_size=1) (weight (Co,Ci,1,1) used in place);
+    relu_in=True computes conv(relu(x)) with the ReLU folded into the operand loads."""
     if conv.bias is not None or conv.kernel_size != (1, 1):
-        return conv(x)
-    return Conv1x1.apply(x, conv.weight, int(conv.stride[0]))
+        return conv(F.relu(x) if relu_in else x)
+    return Conv1x1.apply(x, conv.weight, int(conv.stride[0]), bool(relu_in))

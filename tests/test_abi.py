@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 def test_version_and_error_string():
     from medt_b200 import _cabi
     lib = _cabi.load_library()
-    assert lib.mt_version() == 1
+    assert lib.mt_version() == _cabi.ABI_VERSION == 2
     assert isinstance(lib.mt_last_error(), bytes)
 
 
@@ -87,7 +87,7 @@ def test_misaligned_buffers_are_rejected_before_any_launch():
     p.w_qkv = ctypes.c_void_p(0x1008)
     rc = lib.mt_axial_forward(ctypes.byref(d), ctypes.byref(p), ok, ok, ok, None)
     assert rc == 1 and b"w_qkv" in lib.mt_last_error()
-    rc = lib.mt_up2x_relu_add_forward(1, 4, 4, ok, off, ok, ok, None)
+    rc = lib.mt_up2x_relu_add_forward(1, 1, 4, 4, ok, None, off, ok, ok, None)
     assert rc == 1 and b"aligned" in lib.mt_last_error()
 
 

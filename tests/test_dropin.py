@@ -72,3 +72,45 @@ def test_grouped_bn_matches_sequential_calls():
     assert torch.allclose(a.running_mean, b.running_mean, atol=1e-12)
     assert torch.allclose(a.running_var, b.running_var, atol=1e-12)
     assert int(b.num_batches_tracked) == 4
+
+
+def test_flat_group_adam_equals_per_parameter_adam():
+    """TrainStep re-homes the parameters as views of one flat tensor and runs Adam on that tensor: elementwise the
+    same arithmetic, and a late-activated parameter (the gates of train.py:169-171) gets its own flat tensor with its
+    own step count, as torch.optim.Adam gives a parameter whose first gradient arrives late."""
+    import copy
+    import torch
+    from medt_b200.train_step import FlatGroup
+    torch.manual_seed(0)
+    net_a = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    gate_a = torch.nn.Parameter(torch.tensor(0.1), requires_grad=False)
+    net_b, gate_b = copy.deepcopy(net_a), copy.deepcopy(gate_a)
+    kw = dict(lr=1e-2, weight_decay=1e-3)
+    opt_a = torch.optim.Adam(list(net_a.parameters()) + [gate_a], **kw)
+    g0 = FlatGroup(list(net_b.parameters()))
+    assert all(p.data_ptr() % 16 == 0 for p in g0.params if p.numel() % 4 == 0)
+    opt_b = torch.optim.Adam([g0.flat], **kw)
+    groups = [g0]
+    xs = [torch.randn(4, 6) for _ in range(5)]
+    for it, x in enumerate(xs):
+        if it == 3:                                   # the epoch-10 flip
+            gate_a.requires_grad_(True)
+            gate_b.requires_grad_(True)
+            groups.append(FlatGroup([gate_b]))
+            opt_b.param_groups[0]["params"].append(groups[-1].flat)
+        opt_a.zero_grad(set_to_none=True)
+        (net_a(x) * gate_a).pow(2).sum().backward()
+        opt_a.step()
+        for p in list(net_b.parameters()) + [gate_b]:
+            p.grad = None
+        (net_b(x) * gate_b).pow(2).sum().backward()
+        for g in groups:
+            g.gather_grads_()
+            g.publish_grads_()
+        opt_b.step()
+        for pa, pb in zip(list(net_a.parameters()) + [gate_a], list(net_b.parameters()) + [gate_b]):
+            assert torch.equal(pa.detach(), pb.detach()), it
+    assert int(opt_b.state[groups[0].flat]["step"]) == 5 and int(opt_b.state[groups[1].flat]["step"]) == 2
+    sd = net_b.state_dict()                            # still a normal module: state_dict / load_state_dict work in place
+    net_b.load_state_dict({k: torch.zeros_like(v) for k, v in sd.items()})
+    assert float(groups[0].flat.detach().abs().sum()) == 0.0

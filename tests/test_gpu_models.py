@@ -126,6 +126,45 @@ def test_train_step_graph_equals_eager():
     assert losses[0][1] < losses[0][0]          # it learns on a fixed batch
 
 
+def test_flat_adam_equals_per_parameter_adam_and_survives_recapture():
+    """TrainStep's flat-tensor Adam (1 launch) == torch's per-parameter fused Adam (6 multi-tensor launches), and the
+    epoch-10 gate flip (train.py:169-171) keeps the existing Adam state while the gates start their own step count."""
+    from medt_b200.train_step import TrainStep
+    xs = torch.tensor(fill.image_batch(4, 3, 64), dtype=torch.float32)
+    ys = torch.tensor(fill.mask_batch(4, 64))
+    res = []
+    for flat in (False, True):
+        m = build_filled_model("gated", 64, device="cuda")
+        for n, p in m.named_parameters():                 # the reference starts with frozen gates (axialnet.py:124-127)
+            if n.split(".")[-1] in ("f_qr", "f_kr", "f_sv", "f_sve"):
+                p.requires_grad_(False)
+        ts = TrainStep(m, (4, 3, 64, 64), use_graph=True, flat_adam=flat)
+        out = []
+        for _ in range(2):
+            slot = ts.step(xs, ys)
+            torch.cuda.synchronize()
+            out.append(float(ts.loss_pin[slot]))
+        res.append((out, m.layer1[0].hight_block.qkv_transform.weight.detach().clone(), ts, m))
+    assert np.allclose(res[0][0], res[1][0], rtol=1e-3), (res[0][0], res[1][0])
+    wa, wb = res[0][1], res[1][1]
+    assert (wa - wb).norm() <= 1e-3 * wa.norm()
+    ts, m = res[1][2], res[1][3]
+    assert len(ts.groups) == 1 and m.layer1[0].hight_block.qkv_transform.weight.data_ptr() % 16 == 0
+    gates = [p for n, p in m.named_parameters() if n.split(".")[-1] in ("f_qr", "f_kr", "f_sv", "f_sve")]
+    assert gates and not any(p.requires_grad for p in gates)
+    for p in gates:
+        p.requires_grad_(True)
+    ts.recapture()
+    g_before = gates[0].detach().clone()
+    slot = ts.step(xs, ys)
+    torch.cuda.synchronize()
+    assert len(ts.groups) == 2 and np.isfinite(float(ts.loss_pin[slot]))
+    assert int(ts.opt.state[ts.groups[0].flat]["step"]) == 3 and int(ts.opt.state[ts.groups[1].flat]["step"]) == 1
+    assert not torch.equal(gates[0].detach(), g_before)          # the gates now train
+    # first Adam step of a parameter moves it by ~lr regardless of the gradient scale
+    assert abs(float((gates[0].detach() - g_before).abs()) - ts.lr) < 0.2 * ts.lr
+
+
 def test_logo_patch_generalisation_256px_matches_oracle():
     """SURVEY 8(f)-1: patch = img_size//4 makes `logo` runnable at 256 px (the reference crashes there);
     checked against the oracle's patch loop with the constant substituted (eval mode + train mode)."""

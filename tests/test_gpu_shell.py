@@ -7,24 +7,44 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("shape", [(2, 5, 4, 4), (4, 16, 64, 64), (3, 7, 1, 3), (2, 32, 8, 16)])
+@pytest.mark.parametrize("shape", [(2, 5, 4, 4), (4, 16, 64, 64), (3, 7, 1, 3), (2, 32, 8, 16), (3, 6, 5, 9)])
 @pytest.mark.parametrize("with_skip", [True, False])
-def test_up2x_relu_add_matches_torch(shape, with_skip):
+@pytest.mark.parametrize("with_bias", [True, False])
+def test_up2x_relu_add_matches_torch(shape, with_skip, with_bias):
     from medt_b200.shell_ops import up2x_relu_add
     torch.manual_seed(1)
     n, c, h, w = shape
     x = torch.randn(shape, device="cuda", requires_grad=True)
     skip = torch.randn(n, c, 2 * h, 2 * w, device="cuda", requires_grad=True) if with_skip else None
-    ref = F.relu(F.interpolate(x, scale_factor=(2, 2), mode="bilinear"))
+    bias = torch.randn(c, device="cuda", requires_grad=True) if with_bias else None
+    ref = F.relu(F.interpolate(x + bias[None, :, None, None] if with_bias else x, scale_factor=(2, 2), mode="bilinear"))
     if with_skip:
         ref = ref + skip
-    got = up2x_relu_add(x, skip)
+    got = up2x_relu_add(x, skip, bias)
     assert torch.allclose(got, ref, atol=1e-6, rtol=1e-6)
     d = torch.randn_like(ref)
-    gref = torch.autograd.grad(ref, [x] + ([skip] if with_skip else []), d)
-    ggot = torch.autograd.grad(got, [x] + ([skip] if with_skip else []), d)
+    leaves = [x] + ([skip] if with_skip else []) + ([bias] if with_bias else [])
+    gref = torch.autograd.grad(ref, leaves, d)
+    ggot = torch.autograd.grad(got, leaves, d)
     for a, b in zip(ggot, gref):
-        assert torch.allclose(a, b, atol=1e-5, rtol=1e-5)
+        assert a.shape == b.shape and torch.allclose(a, b, atol=2e-5, rtol=1e-5)
+
+
+def test_decoder_step_with_fused_bias_matches_conv_with_bias():
+    """`_up_relu` runs the decoder conv WITHOUT its bias and lets the fused kernel add it / reduce its gradient."""
+    import lib
+    torch.manual_seed(2)
+    conv = torch.nn.Conv2d(8, 6, kernel_size=3, stride=1, padding=1).cuda()
+    x = torch.randn(2, 8, 16, 16, device="cuda", requires_grad=True)
+    skip = torch.randn(2, 6, 32, 32, device="cuda")
+    ref = F.relu(F.interpolate(conv(x), scale_factor=(2, 2), mode="bilinear")) + skip
+    got = lib.models.axialnet._up_relu(conv, x, skip)
+    assert torch.allclose(got, ref, atol=1e-5, rtol=1e-5)
+    d = torch.randn_like(ref)
+    gr = torch.autograd.grad(ref, (x, conv.weight, conv.bias), d)
+    gg = torch.autograd.grad(got, (x, conv.weight, conv.bias), d)
+    for u, v in zip(gg, gr):
+        assert (u - v).norm() <= 1e-4 * max(v.norm().item(), 1e-3)
 
 
 @pytest.mark.parametrize("n,c,h,w,groups", [(4, 8, 64, 64, 1), (4, 128, 64, 64, 1), (32, 16, 4, 4, 16), (6, 5, 3, 7, 3)])
@@ -59,15 +79,16 @@ def test_bn_act_matches_torch(n, c, h, w, groups, relu, with_res, training):
 
 @pytest.mark.parametrize("n,ci,co,h,w,stride", [(4, 8, 16, 64, 64, 1), (4, 32, 64, 64, 64, 2), (2, 128, 256, 16, 16, 2),
                                                  (64, 64, 128, 4, 4, 1), (3, 5, 7, 6, 10, 1), (2, 16, 32, 5, 7, 2)])
-def test_conv1x1_matches_torch(n, ci, co, h, w, stride):
+@pytest.mark.parametrize("relu_in", [False, True])
+def test_conv1x1_matches_torch(n, ci, co, h, w, stride, relu_in):
     from medt_b200.shell_ops import conv1x1
     torch.manual_seed(3)
     conv = torch.nn.Conv2d(ci, co, kernel_size=1, stride=stride, bias=False).cuda()
     x = torch.randn(n, ci, h, w, device="cuda", requires_grad=True)
     tf32 = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
-    ref = conv(x)
-    got = conv1x1(x, conv)
+    ref = conv(F.relu(x) if relu_in else x)
+    got = conv1x1(x, conv, relu_in=relu_in)
     assert got.shape == ref.shape and torch.allclose(got, ref, atol=1e-5, rtol=1e-5)
     d = torch.randn_like(ref)
     gr = torch.autograd.grad(ref, (x, conv.weight), d)
