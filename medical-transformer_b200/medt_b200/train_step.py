@@ -129,7 +129,12 @@ class TrainStep:
         self.graph = None
         self.opt = None
         self.steps_done = 0
-        self.flat_adam = (not os.environ.get("MEDT_NO_FLAT_ADAM")) if flat_adam is None else bool(flat_adam)
+        # default: flat mode on one GPU; with world_size > 1 the per-parameter optimizer + FlatBucket path (the one
+        # measured on 2 and 4 B200s this round) stays the default until the flat path has run under NCCL -- its host
+        # logic is covered on CPU by tests/test_ddp_gloo.py; pass flat_adam=True to use it.
+        if flat_adam is None:
+            flat_adam = self.world == 1 and not os.environ.get("MEDT_NO_FLAT_ADAM")
+        self.flat_adam = bool(flat_adam)
         self.groups = []
         self._build()
 

@@ -69,6 +69,63 @@ def test_flat_bucket_allreduce_world2_gloo():
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
 
 
+def _worker_flat(rank, world, port, q):
+    """The flat-parameter variant of the step (train_step.FlatGroup): gather -> mean all-reduce of the flat gradient ->
+    Adam on the flat tensor; must equal a per-parameter Adam fed the rank-averaged gradients."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import copy
+        from medt_b200.train_step import FlatGroup, _all_reduce_mean_
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(4, 2, 1))
+        ref = copy.deepcopy(net)
+        group = FlatGroup(list(net.parameters()))
+        opt = torch.optim.Adam([group.flat], lr=1e-2, weight_decay=1e-5)
+        opt_ref = torch.optim.Adam(ref.parameters(), lr=1e-2, weight_decay=1e-5)
+        for it in range(3):
+            torch.manual_seed(100 + 10 * it + rank)            # different data shard per rank
+            x, y = torch.rand(4, 3, 8, 8), torch.randint(0, 2, (4, 8, 8))
+            for p in net.parameters():
+                p.grad = None
+            torch.nn.functional.cross_entropy(net(x), y).backward()
+            group.gather_grads_()
+            _all_reduce_mean_(group.flat.grad, world, None)
+            group.publish_grads_()
+            opt.step()
+            # reference: per-parameter Adam on gradients averaged over the ranks' shards
+            opt_ref.zero_grad(set_to_none=True)
+            torch.nn.functional.cross_entropy(ref(x), y).backward()
+            for p in ref.parameters():
+                dist.all_reduce(p.grad)
+                p.grad.div_(world)
+            opt_ref.step()
+            for a, b in zip(net.parameters(), ref.parameters()):
+                assert torch.allclose(a.detach(), b.detach(), atol=1e-7, rtol=1e-6), it
+        flat = group.flat.detach().clone()
+        both = [torch.zeros_like(flat) for _ in range(world)]
+        dist.all_gather(both, flat)
+        assert torch.equal(both[0], both[1])                   # replicas stay in lock-step
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_group_allreduce_adam_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_flat, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
 def test_reference_script_launcher_paths(tmp_path, monkeypatch):
     """run_reference_script.py: the drop-in `lib` must win over the reference's, while the script's
     bare `import utils / metrics` still resolve in the reference directory."""
