@@ -366,7 +366,36 @@ def run_product(args, rank, world, local_rank):
                                 "host_cores": os.cpu_count() or 1, "kind": "port",
                                 "sample": "3 full train steps (after 1 warm-up) of the same bs=4 128x128 batch",
                                 "ms_per_step": ms_cpu, "cpu": cpu_model_string()}
+    # ---- context only: the reference's op sequence (oracle/torch_port.py, the same checker the CPU baseline times)
+    # run by stock PyTorch eager fp32 on THIS GPU -- SURVEY 8(d) "reference eager on the same B200".  Measured last and
+    # fully guarded so that it can never disturb the numbers above.
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            line["reference_eager_same_gpu"] = reference_eager_gpu(args.model, dev)
+        except Exception as e:  # noqa: BLE001
+            line["reference_eager_same_gpu"] = {"error": repr(e)[:200]}
     print(json.dumps(line), flush=True)
+
+
+def reference_eager_gpu(model_name, dev, steps=10, warmup=3):
+    from oracle import torch_port
+    model = build_model(model_name).to(dev).train()
+    opt = torch.optim.Adam(list(model.parameters()), lr=1e-3, weight_decay=1e-5)
+    x, y = synthetic_batch()
+    x, y = x.to(dev), y.to(dev)
+    for _ in range(warmup):
+        torch_port.train_step(model, opt, x, y)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        torch_port.train_step(model, opt, x, y)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": BS / (ms / 1e3), "unit": "img/s", "ms_per_step": ms, "steps": steps,
+            "what": "oracle/torch_port.py (the reference's ATen op sequence) + torch.optim.Adam, stock PyTorch eager, "
+                    "fp32 (TF32 off), batch resident, no L2 flush -- context, not the reference arm"}
 
 
 def log(*a):
