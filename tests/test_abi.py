@@ -103,6 +103,34 @@ def test_dense_returns_contiguous_aligned_tensors():
     assert _cabi.dense(base.view(6, 6).t()).is_contiguous()
 
 
+def test_ctypes_bindings_match_the_header_prototypes():
+    """Every prototype of include/medt_axial.h against the ctypes argtypes of the host binding: same arity, pointers
+    bound as pointers, int as c_int, float as c_float -- an ABI change that forgets one side fails here, not on a GPU."""
+    import re
+    from medt_b200 import _cabi
+    lib = _cabi.load_library()
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    h = re.sub(r"/\*.*?\*/", "", open(os.path.join(here, "include", "medt_axial.h")).read(), flags=re.S)
+    protos = re.findall(r"\b(?:int|size_t|const char\s*\*)\s*(mt_\w+)\s*\(([^)]*)\)\s*;", h)
+    assert sorted(n for n, _ in protos) == sorted(_cabi.EXPORTS)
+    for name, args in protos:
+        params = [] if args.strip() in ("", "void") else [a.strip() for a in args.split(",")]
+        at = getattr(lib, name).argtypes
+        if not params:
+            assert not at, name
+            continue
+        assert at is not None and len(at) == len(params), (name, len(params), at)
+        for prm, ct in zip(params, at):
+            if "*" in prm:
+                assert ct is ctypes.c_void_p or hasattr(ct, "contents") or issubclass(ct, ctypes._Pointer), (name, prm, ct)
+            elif prm.startswith("float"):
+                assert ct is ctypes.c_float, (name, prm, ct)
+            elif prm.startswith("int"):
+                assert ct is ctypes.c_int, (name, prm, ct)
+            else:
+                raise AssertionError(f"unhandled parameter type in {name}: {prm}")
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     from medt_b200 import _cabi
     monkeypatch.setattr(_cabi, "_LIB", None)
