@@ -7,6 +7,7 @@
 //     y=2 diagonals: d relative[c, i-j+L-1] (one thread per diagonal, scalar walk)
 // P is recomputed from the saved log-sum-exp, dZ = P (dP - D).  Closed forms: oracle/axial_np.py.
 #include "axial_attn2.cuh"
+#include "axial_diag_tile.cuh"
 extern thread_local cudaError_t g_last_cuda;
 
 // Mirror accumulators of WinA / WinB: a pair (r, w) adds its contribution to the slot it read the table
@@ -73,7 +74,10 @@ static size_t bwd2_smem_floats(const Dims& m, int SPB, int nred) {
          (m.pos ? 4 * (size_t)m.gp * rel_pitch(m.L) : 0) + (size_t)SPB * NOC * m.LP + 2 * (size_t)SPB * MT_G * m.L;
 }
 
-template <int D, bool POS, int RT, int MODE>
+// XP: experimental variants of MODE 1, selected at run time by MT_DEBUG_FLAGS bits 3 / 4 (XP = 0 is the measured default
+// and compiles to exactly the kernel profiled in profiles/):  bit 0 = register-tiled wrapped-diagonal pass for d relative
+// (axial_diag_tile.cuh, one diagonal CTA instead of two), bit 1 = rows and columns in separate CTAs (y = 0 / y = 1).
+template <int D, bool POS, int RT, int MODE, int XP = 0>
 __global__ void __launch_bounds__(128)
 k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stats, double* __restrict__ bstats,
        const float* __restrict__ coef, float* __restrict__ bcoef, unsigned* __restrict__ bcnt,
@@ -93,8 +97,10 @@ k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stat
   const int b0 = blockIdx.x * SPB, grp = b0 / m.Bg;
   // MODE 1: CTA y = 0 does the row pass then the column pass on ONE staging of the strips (the kernel is
   // L2-staging bound, profiles/r1_notes.md); y >= 1 are the diagonal-walk CTAs (d relative), split nds ways
-  const bool diag_cta = MODE == 1 && blockIdx.y >= 1;
-  const int dsplit = (int)blockIdx.y - 1, nds = (int)gridDim.y - 1;
+  constexpr bool TDIAG = (XP & 1) && POS && MODE == 1 && D <= 2;
+  constexpr int NMAIN = ((XP & 2) && MODE == 1) ? 2 : 1;
+  const bool diag_cta = MODE == 1 && blockIdx.y >= NMAIN;
+  const int dsplit = (int)blockIdx.y - NMAIN, nds = (int)gridDim.y - NMAIN;
   const int nrel = POS ? 2 * GP * (2 * L - 1) : 0;
   const int nred = MODE == 0 ? 24 : 4 * C + nrel;
   Bwd2Smem s = carve2(m, sm, SPB, nred);
@@ -169,7 +175,9 @@ k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stat
   __syncthreads();
 
   const int nitems = (diag_cta || (m.dbg & 4)) ? 0 : SPB * MT_G * LB;   // dbg bit2: fixed-cost experiment
-  for (int phase = 0; phase < (MODE == 0 ? 1 : 2); ++phase)
+  const int ph_lo = NMAIN == 2 ? (int)blockIdx.y : 0;                   // split variant: CTA y runs pass y only
+  const int ph_hi = MODE == 0 ? 1 : (NMAIN == 2 ? ph_lo + 1 : 2);
+  for (int phase = ph_lo; phase < ph_hi; ++phase)
   for (int base = 0; base < nitems; base += blockDim.x) {
     const int item = base + threadIdx.x;
     const bool act = item < nitems;
@@ -402,8 +410,21 @@ k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stat
       }
     }
   }
-  // ------------------------------------------------------------ diagonals (d relative), scalar walk
-  if (POS && !FOLD && diag_cta) {
+  // ------------------------------------------------------------ diagonals (d relative)
+  if (TDIAG && diag_cta) {          // experimental: register-tiled wrapped diagonals, as many balanced items as the row pass
+    const int nit = SPB * MT_G * LB;
+    const int per = (nit + nds - 1) / nds, i0 = dsplit * per, i1 = i0 + per < nit ? i0 + per : nit;
+    for (int item = i0 + threadIdx.x; item < i1; item += blockDim.x) {
+      const int t = item % LB, g = (item / LB) % MT_G, ss = item / (LB * MT_G);
+      mtdiag::Coefs cf;
+      cf.wqk = s.wsim[g]; cf.wqr = s.wsim[MT_G + g]; cf.wkr = s.wsim[2 * MT_G + g];
+      cf.Aqr = s.sA[MT_G + g]; cf.Bqr = s.sB[MT_G + g]; cf.Cqr = s.sC[MT_G + g];
+      cf.Akr = s.sA[2 * MT_G + g]; cf.Bkr = s.sB[2 * MT_G + g]; cf.Ckr = s.sC[2 * MT_G + g];
+      mtdiag::diag_tile_item<(D <= 2 ? D : 1), RT>(L, LP, RP, t, s.Yn + ((size_t)ss * 2 * C + g * 4 * D) * LP,
+                                                   s.dOs + ((size_t)ss * NOC + g * GP * NO) * LP, s.lses + (ss * MT_G + g) * L,
+                                                   s.Dl + (ss * MT_G + g) * L, s.Rp, cf, dRs);
+    }
+  } else if (POS && !FOLD && diag_cta) {                                   // default: one thread per diagonal, scalar walk
     const int RL = 2 * L - 1, nd = SPB * MT_G * RL;
     const int per = (nd + nds - 1) / nds, i0 = dsplit * per, i1 = i0 + per < nd ? i0 + per : nd;
     for (int item = i0 + threadIdx.x; item < i1; item += blockDim.x) {
@@ -469,10 +490,10 @@ k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stat
 // ---------------------------------------------------------------------------- host side
 int attn2_rt(const Dims& m);
 
-template <int D, bool POS, int RT, int MODE>
-static int launch_b(const Dims& m, const MtAxialParams& p, const MtAxialGrads& gr, const double* stats, double* bstats,
-                    const float* coef, float* bcoef, unsigned* bcnt, const float* yraw, const float* oraw, const float* lse,
-                    const float* gs, float* dyh, cudaStream_t st) {
+template <int D, bool POS, int RT, int MODE, int XP>
+static int launch_bx(const Dims& m, const MtAxialParams& p, const MtAxialGrads& gr, const double* stats, double* bstats,
+                     const float* coef, float* bcoef, unsigned* bcnt, const float* yraw, const float* oraw, const float* lse,
+                     const float* gs, float* dyh, cudaStream_t st) {
   const int LB = m.L / RT;
   int spb = 1;
   while (spb * MT_G * LB < 128 && spb * 2 <= m.Bg && m.Bg % (spb * 2) == 0) spb *= 2;
@@ -481,16 +502,38 @@ static int launch_b(const Dims& m, const MtAxialParams& p, const MtAxialGrads& g
   const size_t smem = bwd2_smem_floats(m, spb, MODE == 0 ? 24 : 4 * m.C + nrel) * sizeof(float);
   if (smem > 200 * 1024) return 0;             // fall back to the v1 kernel
   if (smem > 32 * 1024 &&
-      cudaFuncSetAttribute(k_bwd2<D, POS, RT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      cudaFuncSetAttribute(k_bwd2<D, POS, RT, MODE, XP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return -1;
+  constexpr bool TDIAG = (XP & 1) && POS && MODE == 1 && D <= 2;
+  constexpr int NMAIN = ((XP & 2) && MODE == 1) ? 2 : 1;
 #ifdef MT_FOLD_DREL
-  const dim3 grid(m.B / spb, (MODE == 1 && POS && D > 2) ? 1 + 2 : 1);
+  const int ndiag = (MODE == 1 && POS && D > 2) ? 2 : 0;
 #else
-  const dim3 grid(m.B / spb, (MODE == 1 && POS) ? 1 + 2 : 1);          // y = 0: rows then columns; y = 1, 2: diagonal walk
+  const int ndiag = (MODE == 1 && POS) ? (TDIAG ? 1 : 2) : 0;         // default: y = 0 rows then columns; y = 1, 2 diagonal walk
 #endif
-  k_bwd2<D, POS, RT, MODE><<<grid, 128, smem, st>>>(m, p, gr, stats, bstats, coef, bcoef, bcnt, yraw, oraw, lse, gs, dyh,
-                                                    spb, segw);
+  const dim3 grid(m.B / spb, NMAIN + ndiag);
+  k_bwd2<D, POS, RT, MODE, XP><<<grid, 128, smem, st>>>(m, p, gr, stats, bstats, coef, bcoef, bcnt, yraw, oraw, lse, gs, dyh,
+                                                        spb, segw);
   return 1;
+}
+
+template <int D, bool POS, int RT, int MODE>
+static int launch_b(const Dims& m, const MtAxialParams& p, const MtAxialGrads& gr, const double* stats, double* bstats,
+                    const float* coef, float* bcoef, unsigned* bcnt, const float* yraw, const float* oraw, const float* lse,
+                    const float* gs, float* dyh, cudaStream_t st) {
+#define GX(XX) return launch_bx<D, POS, RT, MODE, XX>(m, p, gr, stats, bstats, coef, bcoef, bcnt, yraw, oraw, lse, gs, dyh, st)
+#ifndef MT_FOLD_DREL
+  if constexpr (MODE == 1) {                      // MT_DEBUG_FLAGS bits 3, 4 -> experimental variants (see k_bwd2)
+    const int xp = (m.dbg >> 3) & 3;
+    if constexpr (POS && D <= 2) {
+      if (xp == 1) { GX(1); }
+      if (xp == 3) { GX(3); }
+    }
+    if (xp & 2) { GX(2); }
+  }
+#endif
+  GX(0);
+#undef GX
 }
 
 // returns launches done (0 = shape not covered -> caller falls back), <0 on error

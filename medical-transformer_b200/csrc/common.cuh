@@ -15,7 +15,7 @@
 struct Dims {
   int N, C, H, W, axis, stride, variant, training, ngroups;
   int nrep;                // accumulator replicas in use: 8 when ngroups < 4, else 1 (groups already spread the atomics)
-  int dbg;                 // MT_DEBUG_FLAGS env (timing experiments only): bit0 = skip global statistic atomics, bit1 = force the v1 attention kernels, bit2 = skip the attention main loops
+  int dbg;                 // MT_DEBUG_FLAGS env (timing experiments only): bit0 = skip global statistic atomics, bit1 = force the v1 attention kernels, bit2 = skip the attention main loops, bit3 = tiled wrapped-diagonal d-relative pass, bit4 = rows / columns of k_bwd2 in separate CTAs (bits 3-4: unmeasured experiments, see axial_attn2_bwd.cu)
   int L, other, B, Bg, gp, d, nt, no, LP, pos;
   float eps, momentum;
   double inv_n1, inv_n2;   // 1/(Bg*L), 1/(Bg*L*L): element counts of the BN1d / BN2d statistics
