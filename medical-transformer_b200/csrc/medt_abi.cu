@@ -31,11 +31,9 @@ static SideStream* side_for_current_device() {
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return nullptr;
   SideStream& ss = g_side[dev];
   if (!ss.ok) {
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;      // never create resources while capturing
     if (cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    (void)cs;
     ss.ok = true;
   }
   return &ss;
