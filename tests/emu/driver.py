@@ -32,6 +32,8 @@ class Grads(C.Structure):
 
 
 def build(out_dir=None, cxx="g++"):
+    if os.environ.get("EMU_LIB"):                            # a prebuilt variant (e.g. -fsanitize=address)
+        return os.environ["EMU_LIB"]
     """Rewrite + compile (only what changed) -> path of libmedt_emu.so."""
     out_dir = out_dir or os.path.join(HERE, "_build")
     srcs = prep.main(out_dir)
@@ -68,6 +70,10 @@ def _buf(a):
 
 
 def _aligned(n_bytes):
+    if os.environ.get("EMU_TIGHT"):                          # exact-size allocations: for runs under AddressSanitizer
+        raw = np.zeros(n_bytes, dtype=np.uint8)
+        assert raw.ctypes.data % 16 == 0
+        return raw
     raw = np.zeros(n_bytes + 64, dtype=np.uint8)
     off = (-raw.ctypes.data) % 64
     return raw[off:off + n_bytes]
