@@ -20,7 +20,7 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
-#define __shared__ static
+#define __shared__ static     /* only for forms prep.py does not rewrite; static __shared__ storage normally becomes emu::cta_shared() */
 
 struct uint3 { unsigned x, y, z; };
 struct dim3 {
@@ -58,8 +58,10 @@ int lin();                                  // linear thread index inside the CT
 int nthreads();
 void barrier_cta();
 void barrier_warp();
-unsigned long long* wslot(int linear_tid);  // 8-byte exchange slot per thread
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+void* cta_shared(const void* key, size_t bytes);   // static __shared__ storage: one fresh, poisoned heap block per CTA and declaration
+unsigned long long exchange(unsigned long long raw, int src_lane_in_warp);   // warp shuffle (all alive lanes of the warp call it)
+int all(int pred);
 }  // namespace emu
 
 #define threadIdx (emu::tid())
@@ -76,29 +78,35 @@ template <class T> static inline T __ldcg(const T* p) { return *p; }
 
 template <class T> static inline T emu_exchange(T v, int src_lane_in_warp) {
   static_assert(sizeof(T) <= 8, "emu shuffle: 8-byte values at most");
-  const int me = emu::lin(), base = me & ~31;
   unsigned long long raw = 0;
   memcpy(&raw, &v, sizeof(T));
-  *emu::wslot(me) = raw;
-  emu::barrier_warp();
-  const int src = base + (src_lane_in_warp & 31);
-  T r = v;
-  if (src < emu::nthreads()) { raw = *emu::wslot(src); memcpy(&r, &raw, sizeof(T)); }
-  emu::barrier_warp();
+  raw = emu::exchange(raw, src_lane_in_warp);
+  T r;
+  memcpy(&r, &raw, sizeof(T));
   return r;
 }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) { return emu_exchange(v, (emu::lin() & 31) ^ lane_mask); }
 template <class T> static inline T __shfl_sync(unsigned, T v, int src_lane) { return emu_exchange(v, src_lane); }
-static inline int __all_sync(unsigned, int pred) {
-  const int me = emu::lin(), base = me & ~31;
-  *emu::wslot(me) = pred ? 1ull : 0ull;
-  emu::barrier_warp();
-  int all = 1;
-  for (int l = base; l < base + 32 && l < emu::nthreads(); ++l) all &= (int)*emu::wslot(l);
-  emu::barrier_warp();
-  return all;
+static inline int __all_sync(unsigned, int pred) { return emu::all(pred); }
+// atomics go through the compiler builtins so that ThreadSanitizer (tests/emu/run_tsan.sh) sees them as atomics
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline float atomicAdd(float* p, float v) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(p);
+  uint32_t old = __atomic_load_n(u, __ATOMIC_SEQ_CST), nw;
+  float f;
+  do { memcpy(&f, &old, 4); f += v; memcpy(&nw, &f, 4); } while (!__atomic_compare_exchange_n(u, &old, nw, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+  memcpy(&f, &old, 4);
+  return f;
 }
-template <class T> static inline T atomicAdd(T* p, T v) { const T old = *p; *p = old + v; return old; }
+static inline double atomicAdd(double* p, double v) {
+  uint64_t* u = reinterpret_cast<uint64_t*>(p);
+  uint64_t old = __atomic_load_n(u, __ATOMIC_SEQ_CST), nw;
+  double f;
+  do { memcpy(&f, &old, 8); f += v; memcpy(&nw, &f, 8); } while (!__atomic_compare_exchange_n(u, &old, nw, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+  memcpy(&f, &old, 8);
+  return f;
+}
 
 template <class T> static inline T min(T a, T b) { return a < b ? a : b; }
 template <class T> static inline T max(T a, T b) { return a > b ? a : b; }

@@ -93,10 +93,38 @@ def rewrite_bodies(s):
     return s
 
 
+def rewrite_static_shared(text):
+    """`__shared__ [__align__(n)] T a[N], b[M][K];`  ->  references to per-CTA heap blocks from emu::cta_shared()
+    (fresh + poisoned for every CTA; each array its own allocation, so AddressSanitizer sees overruns and
+    ThreadSanitizer starts every CTA with clean race state)."""
+    out = []
+    for line in text.split("\n"):
+        m = re.match(r"^(\s*)__shared__\s+(?:__align__\(\d+\)\s+)?(.*);\s*$", line)
+        if not m or "extern" in line:
+            out.append(line)
+            continue
+        pieces = _split_top(m.group(2))
+        first = re.match(r"^(\w+)\s+(\w+)((?:\[[^\]]*\])*)$", pieces[0])
+        assert first, line
+        typ = first.group(1)
+        decls = [(first.group(2), first.group(3))]
+        for pc in pieces[1:]:
+            mm = re.match(r"^(\w+)((?:\[[^\]]*\])*)$", pc)
+            assert mm, line
+            decls.append((mm.group(1), mm.group(2)))
+        stm = []
+        for name, dims in decls:
+            stm.append(f"typedef {typ} emu_t_{name}{dims}; static char emu_k_{name}; "
+                       f"emu_t_{name}& {name} = *reinterpret_cast<emu_t_{name}*>(emu::cta_shared(&emu_k_{name}, sizeof(emu_t_{name})));")
+        out.append(m.group(1) + " ".join(stm))
+    return "\n".join(out)
+
+
 def convert(text):
     text = text.replace('#include "../../include/medt_axial.h"', f'#include "{os.path.join(ROOT, "include", "medt_axial.h")}"')
     text = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?float\s+(\w+)\[\];",
                   r"float* \1 = reinterpret_cast<float*>(emu::g_dyn_smem);", text)
+    text = rewrite_static_shared(text)
     text = rewrite_bodies(text)
     text = rewrite_launches(text)
     assert "<<<" not in text and "asm volatile" not in text.split("__CUDA_ARCH__")[0], "unconverted CUDA construct"
