@@ -145,3 +145,42 @@ def test_conv1x1_kernels_under_emulation(emu_lib, n, ci, co, h, w, stride, relu_
     assert emu_lib.mt_conv1x1_backward(n, ci, co, h, w, stride, int(relu_in), _ptr(xs), _ptr(ws), _ptr(_f32(d)), _ptr(dx), _ptr(dw), None) == 0
     assert np.allclose(dx, g_ref[0].numpy(), atol=2e-5, rtol=1e-4)
     assert np.allclose(dw, g_ref[1].reshape(co, ci).numpy(), atol=2e-5, rtol=1e-4)
+
+
+def _golden_names():
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    sys.path.insert(0, HERE)
+    import helpers
+    return helpers.op_fixture_names()
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+@pytest.mark.parametrize("name", _golden_names())
+def test_emulated_kernels_match_the_reference_goldens(emu_lib, name, mode):
+    """The same fixtures the `-m gpu` tier checks (produced by executing the REFERENCE in fp64, tests/golden/make_golden.py):
+    outputs, every gradient and the updated running statistics, here through the emulated kernels."""
+    import driver
+    import helpers
+    z, p, cfg = helpers.load_op(name)
+    training = mode == "train"
+    out, g, run = driver.run_axial(emu_lib, z["x"], p, cfg["axis"], cfg["stride"], cfg["variant"], training, cfg["ngroups"], z["dout"])
+    rel = helpers.rel_err
+    errs = {"out": rel(out, z[f"{mode}_out"]), "dx": rel(g["dx"], z[f"{mode}_dx"])}
+    gk = lambda k: z[f"{mode}_grad.{k}"]  # noqa: E731
+    errs["dw_qkv"] = rel(g["dw_qkv"].reshape(-1), gk("qkv_transform.weight").reshape(-1))
+    for short, bn in (("bn_qkv", "bn_qkv"), ("bn_out", "bn_output")):
+        errs["d" + short + "_w"] = rel(g["d" + short + "_w"], gk(bn + ".weight"))
+        errs["d" + short + "_b"] = rel(g["d" + short + "_b"], gk(bn + ".bias"))
+    errs["dbn_sim_w"] = rel(g["dbn_sim_w"], gk("bn_similarity.weight"))
+    scale = max(float(np.abs(gk("bn_similarity.weight")).max()), 1e-30)
+    errs["dbn_sim_b"] = float(np.abs(g["dbn_sim_b"] - gk("bn_similarity.bias")).max()) / scale      # identically zero in exact arithmetic
+    if cfg["variant"] != "nopos":
+        errs["drelative"] = rel(g["drelative"], gk("relative"))
+    if cfg["variant"] == "gated":
+        want = np.array([float(gk(k)) for k in ("f_qr", "f_kr", "f_sv", "f_sve")])
+        errs["dgates"] = rel(g["dgates"], want)
+    if training:
+        for short, bn in (("bn_qkv", "bn_qkv"), ("bn_sim", "bn_similarity"), ("bn_out", "bn_output")):
+            errs[short + "_rm"] = rel(run[short + "_rm"], z[f"train_buf.{bn}.running_mean"])
+            errs[short + "_rv"] = rel(run[short + "_rv"], z[f"train_buf.{bn}.running_var"])
+    assert max(errs.values()) < 5e-5, errs
