@@ -215,13 +215,15 @@ __device__ __forceinline__ bool last_cta_done(unsigned* counter, unsigned total)
 __device__ __forceinline__ float gate_val(const float* p) { return p ? __ldg(p) : 1.f; }
 
 // ---- forward coefficient finalisers (all threads of ONE CTA) ---------------------------------
+// (training: the running statistics are NOT read here -- with ngroups > 1 another thread's ema_update() below writes the
+//  same channel without a barrier in between; tests/emu/run_tsan.sh found that read, which bn_coef ignored anyway)
 __device__ __forceinline__ void fin_qkv(const Dims& m, const MtAxialParams& p, const double* stats, float* coef) {
   const double n = m.inv_n1;
   for (int k = threadIdx.x; k < m.ngroups * 2 * m.C; k += blockDim.x) {
     const int g = k / (2 * m.C), ch = k - g * 2 * m.C;
     BnCoef c = bn_coef(m.training, m.training ? stat_get(m, stats, g, m.nstat_f, m.f_qkv_sum + ch) : 0.0,
                        m.training ? stat_get(m, stats, g, m.nstat_f, m.f_qkv_sq + ch) : 0.0, n, 1.f, p.bn_qkv_w[ch],
-                       p.bn_qkv_b[ch], p.bn_qkv_rm[ch], p.bn_qkv_rv[ch], m.eps);
+                       p.bn_qkv_b[ch], m.training ? 0.f : p.bn_qkv_rm[ch], m.training ? 1.f : p.bn_qkv_rv[ch], m.eps);
     float* o = coef + (size_t)g * m.ncoef_f + m.cf_q + 2 * ch;
     o[0] = c.a; o[1] = c.b;
   }
@@ -237,7 +239,7 @@ __device__ __forceinline__ void fin_sim(const Dims& m, const MtAxialParams& p, c
     const float f = t == 0 ? 1.f : (t == 1 ? gate_val(p.f_qr) : gate_val(p.f_kr));
     BnCoef c = bn_coef(m.training, m.training ? stat_get(m, stats, g, m.nstat_f, m.f_sim_sum + ch) : 0.0,
                        m.training ? stat_get(m, stats, g, m.nstat_f, m.f_sim_sq + ch) : 0.0, n, f, p.bn_sim_w[ch],
-                       p.bn_sim_b[ch], p.bn_sim_rm[ch], p.bn_sim_rv[ch], m.eps);
+                       p.bn_sim_b[ch], m.training ? 0.f : p.bn_sim_rm[ch], m.training ? 1.f : p.bn_sim_rv[ch], m.eps);
     float* o = coef + (size_t)g * m.ncoef_f + m.cf_s + 2 * ch;
     o[0] = c.a * MT_LOG2E; o[1] = c.a;
   }
@@ -256,7 +258,7 @@ __device__ __forceinline__ void fin_out(const Dims& m, const MtAxialParams& p, c
     const float f = (m.no == 2 && (ch & 1)) ? gate_val(p.f_sve) : gate_val(p.f_sv);
     BnCoef c = bn_coef(m.training, m.training ? stat_get(m, stats, g, m.nstat_f, m.f_out_sum + ch) : 0.0,
                        m.training ? stat_get(m, stats, g, m.nstat_f, m.f_out_sq + ch) : 0.0, n, f, p.bn_out_w[ch],
-                       p.bn_out_b[ch], p.bn_out_rm[ch], p.bn_out_rv[ch], m.eps);
+                       p.bn_out_b[ch], m.training ? 0.f : p.bn_out_rm[ch], m.training ? 1.f : p.bn_out_rv[ch], m.eps);
     float* o = coef + (size_t)g * m.ncoef_f + m.cf_o + 2 * ch;
     o[0] = c.a; o[1] = c.b;
   }
