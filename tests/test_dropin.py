@@ -114,3 +114,31 @@ def test_flat_group_adam_equals_per_parameter_adam():
     sd = net_b.state_dict()                            # still a normal module: state_dict / load_state_dict work in place
     net_b.load_state_dict({k: torch.zeros_like(v) for k, v in sd.items()})
     assert float(groups[0].flat.detach().abs().sum()) == 0.0
+
+
+def test_inference_helpers_threshold_and_checkpoint_prefix(tmp_path):
+    """medt_b200.infer: the reference's thresholding (test.py:124-146) and `module.`-prefix tolerant checkpoint loading."""
+    import numpy as np
+    import torch
+    import lib
+    from medt_b200.infer import Predictor, load_checkpoint, logits_to_mask
+    torch.manual_seed(0)
+    logits = torch.randn(3, 2, 5, 7)
+    logits[0, 1, 0, 0] = 0.5                                    # boundary: >= 0.5 is foreground
+    tmp = logits.numpy().copy()                                  # the reference's numpy sequence
+    tmp[tmp >= 0.5] = 1
+    tmp[tmp < 0.5] = 0
+    want = tmp.astype(int)
+    want[want == 1] = 255
+    got = logits_to_mask(logits)
+    assert got.dtype == torch.uint8 and np.array_equal(got.numpy(), want[:, 1])
+    m = lib.models.axialnet.gated(img_size=32, imgchan=3)
+    ref_state = {k: torch.randn_like(v) if v.is_floating_point() else v.clone() for k, v in m.state_dict().items()}
+    torch.save({"module." + k: v for k, v in ref_state.items()}, tmp_path / "dp.pth")       # written under DataParallel
+    load_checkpoint(m, str(tmp_path / "dp.pth"))
+    assert all(torch.equal(v, ref_state[k]) for k, v in m.state_dict().items())
+    dp = torch.nn.DataParallel(lib.models.axialnet.gated(img_size=32, imgchan=3))
+    load_checkpoint(dp, ref_state)                                                            # plain -> wrapped model
+    assert all(torch.equal(v, ref_state[k[len("module."):]]) for k, v in dp.state_dict().items())
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        Predictor(m, (1, 3, 32, 32))

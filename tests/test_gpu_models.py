@@ -8,6 +8,8 @@ Tolerances (BASELINE north_star: logits within 1e-2 relative, exact masks):
   eval mode   logits rel-L2 < 1e-4
   masks       `logit_1 >= 0.5` (train.py:143-145) and argmax must agree wherever the golden
               margin exceeds 20x the largest logit error we allow the fp32 path."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -163,6 +165,37 @@ def test_flat_adam_equals_per_parameter_adam_and_survives_recapture():
     assert not torch.equal(gates[0].detach(), g_before)          # the gates now train
     # first Adam step of a parameter moves it by ~lr regardless of the gradient scale
     assert abs(float((gates[0].detach() - g_before).abs()) - ts.lr) < 0.2 * ts.lr
+
+
+def test_predictor_masks_equal_thresholded_eval_logits(tmp_path):
+    """medt_b200.infer.Predictor: host batch in, 0/255 uint8 masks out == the reference's numpy thresholding of the
+    eval-mode logits (test.py:124-146); PNG round trip through cv2."""
+    import cv2
+    from medt_b200.infer import Predictor
+    m = build_filled_model("gated", 64, device="cuda").eval()
+    xs = torch.tensor(fill.image_batch(2, 3, 64), dtype=torch.float32)
+    with torch.no_grad():
+        logits = m(xs.cuda()).cpu().numpy()
+    tmp = logits.copy()
+    tmp[tmp >= 0.5] = 1
+    tmp[tmp < 0.5] = 0
+    want = (tmp.astype(int)[:, 1] * 255).astype(np.uint8)
+    pred = Predictor(m, (2, 3, 64, 64))
+    got = pred.predict(xs).numpy().copy()
+    # identical kernels and inputs; a logit within float noise of 0.5 may flip between two runs (statistic atomics order)
+    assert (got != want).mean() < 1e-3
+    pred.save_png(torch.from_numpy(got), ["001.png", "002.png"], str(tmp_path))
+    assert np.array_equal(cv2.imread(str(tmp_path / "002.png"), cv2.IMREAD_GRAYSCALE), got[1])
+
+
+@pytest.mark.skipif(os.environ.get("MEDT_EXPERIMENTAL") != "1", reason="opt-in: MEDT_EXPERIMENTAL=1 (graph-captured inference not yet run on a GPU)")
+def test_predictor_graph_equals_eager():
+    from medt_b200.infer import Predictor
+    m = build_filled_model("gated", 64, device="cuda").eval()
+    xs = torch.tensor(fill.image_batch(2, 3, 64), dtype=torch.float32)
+    a = Predictor(m, (2, 3, 64, 64), use_graph=False).predict(xs).numpy().copy()
+    b = Predictor(m, (2, 3, 64, 64), use_graph=True).predict(xs).numpy().copy()
+    assert (a != b).mean() < 1e-3
 
 
 def test_logo_patch_generalisation_256px_matches_oracle():
