@@ -10,46 +10,6 @@
 #include "axial_diag_tile.cuh"
 extern thread_local cudaError_t g_last_cuda;
 
-// Mirror accumulators of WinA / WinB: a pair (r, w) adds its contribution to the slot it read the table
-// value from; after each step one RT-block is complete for this thread and is flushed to the CTA's
-// shared-memory d relative accumulator (plain index m).  This replaces the separate diagonal walk.
-template <int RT>
-struct AccA {            // pairs index  own - walk + L - 1 ; slot layout of WinA (hi = block K, lo = block K-1)
-  float hi[RT], lo[RT];
-  __device__ __forceinline__ void zero() {
-#pragma unroll
-    for (int k = 0; k < RT; ++k) { hi[k] = 0.f; lo[k] = 0.f; }
-  }
-  __device__ __forceinline__ void add(int r, int w, float v) { const int d = r - w; if (d >= 1) hi[d - 1] += v; else lo[RT - 1 + d] += v; }
-  // after a step: block K (hi) is finished; afterwards hi <- lo, lo <- 0
-  __device__ __forceinline__ void flush_step(float* row, int K, int RL) {
-#pragma unroll
-    for (int k = 0; k < RT; ++k) { const int mm = RT * K + k; if (mm < RL) atomicAdd(row + mm, hi[k]); hi[k] = lo[k]; lo[k] = 0.f; }
-  }
-  __device__ __forceinline__ void flush_end(float* row, int K, int RL) {     // remaining block K (now in hi)
-#pragma unroll
-    for (int k = 0; k < RT; ++k) { const int mm = RT * K + k; if (mm >= 0 && mm < RL) atomicAdd(row + mm, hi[k]); }
-  }
-};
-template <int RT>
-struct AccB {            // pairs index  walk - own + L - 1 ; shifted slots x = m + 1 (lo = block K-1, hi = block K)
-  float lo[RT], hi[RT];
-  __device__ __forceinline__ void zero() {
-#pragma unroll
-    for (int k = 0; k < RT; ++k) { hi[k] = 0.f; lo[k] = 0.f; }
-  }
-  __device__ __forceinline__ void add(int r, int w, float v) { const int d = w - r; if (d >= 0) hi[d] += v; else lo[RT + d] += v; }
-  // after a step: block K-1 (lo) is finished; afterwards lo <- hi, hi <- 0
-  __device__ __forceinline__ void flush_step(float* row, int K, int RL) {
-#pragma unroll
-    for (int k = 0; k < RT; ++k) { const int mm = RT * (K - 1) + k - 1; if (mm >= 0 && mm < RL) atomicAdd(row + mm, lo[k]); lo[k] = hi[k]; hi[k] = 0.f; }
-  }
-  __device__ __forceinline__ void flush_end(float* row, int K, int RL) {     // remaining block K (now in lo)
-#pragma unroll
-    for (int k = 0; k < RT; ++k) { const int mm = RT * K + k - 1; if (mm >= 0 && mm < RL) atomicAdd(row + mm, lo[k]); }
-  }
-};
-
 struct Bwd2Smem {
   float *ca, *cb, *wsim, *sA, *sB, *sC, *oA, *oB, *oC, *red, *Yn, *Rp, *Rs, *dOs, *Dl, *lses;
 };
@@ -84,14 +44,9 @@ k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stat
        const float* __restrict__ yraw, const float* __restrict__ oraw, const float* __restrict__ lse,
        const float* __restrict__ gs, float* __restrict__ dyh, int SPB, int segw) {
   constexpr int GP = 2 * D, NO = POS ? 2 : 1;
-  // d relative: default = concurrent diagonal-walk CTAs (blockIdx.y >= 1).  -DMT_FOLD_DREL accumulates it inside the
-  // row pass instead (mirror window accumulators, no extra pair evaluations) -- measured 2.4 % slower at 128 px and
-  // 10 % slower at 512 px because of its bank-conflicted shared-memory atomics (profiles/r1_notes.md).
-#ifdef MT_FOLD_DREL
-  constexpr bool FOLD = POS && MODE == 1 && D <= 2;
-#else
-  constexpr bool FOLD = false;
-#endif
+  // d relative: concurrent diagonal CTAs (blockIdx.y >= NMAIN).  Accumulating it inside the row pass instead (mirror window
+  // accumulators flushed with shared-memory atomics) was measured 2.4 % slower at 128 px and 10 % at 512 px and removed
+  // (profiles/r1_notes.md item 10).
   extern __shared__ __align__(16) float sm[];
   const int C = m.C, L = m.L, LP = m.LP, NOC = NO * C, RP = rel_pitch(L), LB = L / RT;
   const int b0 = blockIdx.x * SPB, grp = b0 / m.Bg;
@@ -218,13 +173,6 @@ k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stat
       for (int c = 0; c < D; ++c)
 #pragma unroll
         for (int r = 0; r < RT; ++r) dq[c][r] = 0.f;
-      AccA<RT> aRq[FOLD ? D : 1]; AccB<RT> aRk[FOLD ? D : 1]; AccA<RT> aRv[FOLD ? GP : 1];
-      if (FOLD) {
-#pragma unroll
-        for (int c = 0; c < D; ++c) { aRq[c].zero(); aRk[c].zero(); }
-#pragma unroll
-        for (int c = 0; c < GP; ++c) aRv[c].zero();
-      }
       for (int wb = 0; wb < LB; ++wb) {
         float kk[D][RT], vv[GP][RT];
 #pragma unroll
@@ -261,35 +209,14 @@ k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stat
                 dq[c][r] = fmaf(dSqk, kk[c][w], dq[c][r]);
                 if (POS) dq[c][r] = fmaf(dSqr, wq[c].get(r, w), dq[c][r]);
               }
-              if (FOLD && act) {
-                const float dSkr = fmaf(Akr, dZ, fmaf(Ckr, skr, Bkr));
-#pragma unroll
-                for (int c = 0; c < D; ++c) { aRq[c].add(r, w, dSqr * q[c][r]); aRk[c].add(r, w, dSkr * kk[c][w]); }
-#pragma unroll
-                for (int c = 0; c < GP; ++c) aRv[c].add(r, w, P * dse[c][r]);
-              }
             }
           }
-        if (FOLD) {      // the block that just left the window is complete for this thread: flush it
-          const int RL = 2 * L - 1;
-#pragma unroll
-          for (int c = 0; c < D; ++c) { aRq[c].flush_step(dRs + c * RL, KA0 - wb, RL); aRk[c].flush_step(dRs + (D + c) * RL, KB0 + wb, RL); }
-#pragma unroll
-          for (int c = 0; c < GP; ++c) aRv[c].flush_step(dRs + (GP + c) * RL, KA0 - wb, RL);
-        }
         if (POS && wb + 1 < LB) {
 #pragma unroll
           for (int c = 0; c < D; ++c) { wq[c].advance(s.Rp + c * RP, KA0 - wb - 1); wk[c].advance(s.Rs + (D + c) * RP, KB0 + wb + 1); }
 #pragma unroll
           for (int c = 0; c < GP; ++c) wv[c].advance(s.Rp + (GP + c) * RP, KA0 - wb - 1);
         }
-      }
-      if (FOLD) {
-        const int RL = 2 * L - 1;
-#pragma unroll
-        for (int c = 0; c < D; ++c) { aRq[c].flush_end(dRs + c * RL, KA0 - LB, RL); aRk[c].flush_end(dRs + (D + c) * RL, KB0 + LB - 1, RL); }
-#pragma unroll
-        for (int c = 0; c < GP; ++c) aRv[c].flush_end(dRs + (GP + c) * RL, KA0 - LB, RL);
       }
       if (MODE == 0) {
         if (!act) { t0 = t1 = t2 = 0.f; }
@@ -424,7 +351,7 @@ k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stat
                                                    s.dOs + ((size_t)ss * NOC + g * GP * NO) * LP, s.lses + (ss * MT_G + g) * L,
                                                    s.Dl + (ss * MT_G + g) * L, s.Rp, cf, dRs);
     }
-  } else if (POS && !FOLD && diag_cta) {                                   // default: one thread per diagonal, scalar walk
+  } else if (POS && diag_cta) {                                   // default: one thread per diagonal, scalar walk
     const int RL = 2 * L - 1, nd = SPB * MT_G * RL;
     const int per = (nd + nds - 1) / nds, i0 = dsplit * per, i1 = i0 + per < nd ? i0 + per : nd;
     for (int item = i0 + threadIdx.x; item < i1; item += blockDim.x) {
@@ -477,7 +404,7 @@ k_bwd2(Dims m, MtAxialParams p, MtAxialGrads gr, const double* __restrict__ stat
         MT_GADD(m, bs + m.b_qkv_s1 + ch, (double)s.red[ch * 2]);
         MT_GADD(m, bs + m.b_qkv_s2 + ch, (double)s.red[ch * 2 + 1]);
       }
-    if (POS && (FOLD ? !diag_cta : diag_cta))
+    if (POS && diag_cta)
       for (int k = threadIdx.x; k < nrel; k += blockDim.x) MT_GADD(m, gr.drelative + k, dRs[k]);
     // last CTA of all passes: bn_qkv backward coefficients for the projection GEMMs + every BN / gate gradient
     if (last_cta_done(bcnt + 2, gridDim.x * gridDim.y)) {
@@ -506,11 +433,7 @@ static int launch_bx(const Dims& m, const MtAxialParams& p, const MtAxialGrads& 
     return -1;
   constexpr bool TDIAG = (XP & 1) && POS && MODE == 1 && D <= 2;
   constexpr int NMAIN = ((XP & 2) && MODE == 1) ? 2 : 1;
-#ifdef MT_FOLD_DREL
-  const int ndiag = (MODE == 1 && POS && D > 2) ? 2 : 0;
-#else
   const int ndiag = (MODE == 1 && POS) ? (TDIAG ? 1 : 2) : 0;         // default: y = 0 rows then columns; y = 1, 2 diagonal walk
-#endif
   const dim3 grid(m.B / spb, NMAIN + ndiag);
   k_bwd2<D, POS, RT, MODE, XP><<<grid, 128, smem, st>>>(m, p, gr, stats, bstats, coef, bcoef, bcnt, yraw, oraw, lse, gs, dyh,
                                                         spb, segw);
@@ -522,7 +445,6 @@ static int launch_b(const Dims& m, const MtAxialParams& p, const MtAxialGrads& g
                     const float* coef, float* bcoef, unsigned* bcnt, const float* yraw, const float* oraw, const float* lse,
                     const float* gs, float* dyh, cudaStream_t st) {
 #define GX(XX) return launch_bx<D, POS, RT, MODE, XX>(m, p, gr, stats, bstats, coef, bcoef, bcnt, yraw, oraw, lse, gs, dyh, st)
-#ifndef MT_FOLD_DREL
   if constexpr (MODE == 1) {                      // MT_DEBUG_FLAGS bits 3, 4 -> experimental variants (see k_bwd2)
     const int xp = (m.dbg >> 3) & 3;
     if constexpr (POS && D <= 2) {
@@ -531,7 +453,6 @@ static int launch_b(const Dims& m, const MtAxialParams& p, const MtAxialGrads& g
     }
     if (xp & 2) { GX(2); }
   }
-#endif
   GX(0);
 #undef GX
 }
