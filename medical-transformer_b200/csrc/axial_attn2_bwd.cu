@@ -1,10 +1,11 @@
 // axial_attn2_bwd.cu -- register-tiled backward attention passes (layout of axial_attn2.cuh):
 //   MODE 0  T[t,g] = sum dZ * S_t                       (bn_similarity backward needs it first)
-//   MODE 1  gradients; blockIdx.y picks the pass so the three run concurrently:
-//     y=0 rows, then columns on the same staging: dq[c,i] = sum_j dS_qk k[c,j] + dS_qr Rq[c,i-j]           (thread owns RT rows)
-//     y=1 columns: dk[c,j] = sum_i dS_qk q[c,i] + dS_kr Rk[c,j-i] ; dv[c,j] = sum_i P dO_sv[c,i]
-//                                                                           (thread owns RT columns)
-//     y=2 diagonals: d relative[c, i-j+L-1] (one thread per diagonal, scalar walk)
+//   MODE 1  gradients; blockIdx.y picks the pass, all CTAs of one strip group run concurrently:
+//     y=0    rows:    dq[c,i] = sum_j dS_qk k[c,j] + dS_qr Rq[c,i-j]                                   (thread owns RT rows)
+//            then, on the same staging,
+//            columns: dk[c,j] = sum_i dS_qk q[c,i] + dS_kr Rk[c,j-i] ; dv[c,j] = sum_i P dO_sv[c,i]     (thread owns RT columns)
+//     y=1,2  diagonals: d relative[c, i-j+L-1], one thread per diagonal (scalar walk), half of the diagonals each
+//   (experimental layouts behind MT_DEBUG_FLAGS bits 3 / 4: see the XP template parameter of k_bwd2)
 // P is recomputed from the saved log-sum-exp, dZ = P (dP - D).  Closed forms: oracle/axial_np.py.
 #include "axial_attn2.cuh"
 #include "axial_diag_tile.cuh"
