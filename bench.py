@@ -366,14 +366,14 @@ def run_product(args, rank, world, local_rank):
                                 "host_cores": os.cpu_count() or 1, "kind": "port",
                                 "sample": "3 full train steps (after 1 warm-up) of the same bs=4 128x128 batch",
                                 "ms_per_step": ms_cpu, "cpu": cpu_model_string()}
-    # ---- context only: the reference's op sequence (oracle/torch_port.py, the same checker the CPU baseline times)
-    # run by stock PyTorch eager fp32 on THIS GPU -- SURVEY 8(d) "reference eager on the same B200".  Measured last and
-    # fully guarded so that it can never disturb the numbers above.
+    # ---- still the baseline leg: the same checker (oracle/torch_port.py, the reference's op sequence) run by stock PyTorch
+    # eager fp32 on THIS GPU -- SURVEY 8(d) "reference eager on the same B200".  Context next to the CPU number, measured
+    # last and fully guarded so that it can never disturb the numbers above; never the reference arm.
     if world == 1 and not args.no_cpu_baseline:
         try:
-            line["reference_eager_same_gpu"] = reference_eager_gpu(args.model, dev)
+            line["cpu_baseline"]["same_gpu_eager"] = reference_eager_gpu(args.model, dev)
         except Exception as e:  # noqa: BLE001
-            line["reference_eager_same_gpu"] = {"error": repr(e)[:200]}
+            line["cpu_baseline"]["same_gpu_eager"] = {"error": repr(e)[:200]}
     print(json.dumps(line), flush=True)
 
 
