@@ -1,0 +1,72 @@
+// axial_coop.cuh -- persistent cooperative ("one launch per op direction") kernels: shared plan, grid barrier, launch.
+//
+// Round 1 ran one axial op as 4 forward + 5 backward launches; each of the three batch-statistics BatchNorms inside the
+// op (reference axialnet.py:151,167,179) was a kernel boundary, and y_raw / o_raw / g_s / dy went through L2/HBM between
+// them (ncu: 6.1x the algorithmic DRAM bytes, ~10 us fixed cost per launch).  Here ONE cooperative launch walks all
+// phases; the grid-wide dependency of each BatchNorm is a grid barrier (~0.5 us: one L2 atomic + an acquire spin), and a
+// CTA keeps the q/k/v rows of its strips RESIDENT in shared memory across the phases whenever its share of the op fits
+// (always at 128 px; at 512 px the kernel streams units through one slot and re-reads its own y_raw from L2).
+//
+// Work unit = SPU consecutive strips x one head group (8/HS heads).  Heads are independent from the projection onwards
+// (output channel o = g*2gp + r belongs to head g, axialnet.py:152), so small-batch layers (B = 64 strips at L = 16) are
+// split over heads to fill the 148 SMs.  Unit u = strip_block*HS + head_group runs on CTA u % G; G is a multiple of HS,
+// so a CTA always serves the same head group and stages its slice of W_qkv once.
+#pragma once
+#include "axial_attn2.cuh"
+
+#define MT_COOP_THREADS 256
+
+template <> struct VecT<1> { typedef float T; };
+
+struct CoopPlan {
+  int G;                 // CTAs (all co-resident: cooperative launch)
+  int SPU, HS, HPU;      // strips per unit, head split, heads per unit
+  int RU, CU, NOCU;      // rows of y (q|k|v of the unit's heads), output channels, o_raw channels per unit
+  int RT, KS, LB;        // rows per thread, key split (lanes sharing a row block), L / RT
+  int XP;                // SPU * L positions per unit
+  int nunits, upc, nslot, resident;
+  int tm, tn;            // projection GEMM thread tile
+  int WTP;               // pitch of the transposed W slice
+  // shared-memory carve (float offsets)
+  int o_ca, o_cb, o_wsim, o_oa, o_ob, o_redq, o_reds, o_redo, o_tab, o_rp, o_rs, o_wt, o_x, o_slot;
+  int ys_fl, slot_fl, tab_fl;
+  size_t smem_bytes;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Grid barrier of a cooperative launch.  `bar` is a zero-initialised counter in the op's own buffer (zeroed with the
+// statistic accumulators); epoch e is complete when the counter reaches e * nctas.  Arrive = fence + relaxed atomic,
+// wait = acquire load spin by one thread; a lost CTA traps instead of hanging the device.
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nctas, unsigned& epoch) {
+  ++epoch;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    const unsigned target = epoch * nctas;
+    unsigned v = 0;
+    const long long t0 = clock64();
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+      if (v >= target) break;
+      if (clock64() - t0 > (1ll << 31)) __trap();
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// cooperative launch; arguments are passed as lvalues of exactly the kernel's parameter types.
+// (the CPU emulation tier of tests/emu pre-defines this macro with its own co-scheduled launch)
+#ifndef MT_COOP_LAUNCH
+template <typename... A>
+static inline cudaError_t coop_launch_(const void* k, dim3 g, dim3 b, size_t smem, cudaStream_t st, A&... a) {
+  void* args[] = {(void*)&a...};
+  return cudaLaunchCooperativeKernel(k, g, b, args, smem, st);
+}
+#define MT_COOP_LAUNCH(kern, grid, block, smem, stream, ...) \
+  (g_last_cuda = coop_launch_((const void*)(kern), dim3(grid), dim3(block), (size_t)(smem), (stream), __VA_ARGS__))
+#endif
+
+int coop_sm_count();
+int coop_max_ctas_env();

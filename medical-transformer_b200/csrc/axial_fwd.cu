@@ -203,6 +203,8 @@ k_attn(Dims m, MtAxialParams p, const float* __restrict__ yraw, double* __restri
 int launch_proj(const Dims& m, const MtAxialParams& p, const float* x, float* yraw, double* stats, float* coef,
                 unsigned* cnt, cudaStream_t st);
 int launch_out(const Dims& m, const float* coef, const float* oraw, float* out, cudaStream_t st);
+int launch_coop_fwd(const Dims& m, const MtAxialParams& p, const float* x, float* out, double* stats, float* coef,
+                    unsigned* cnt, float* yraw, float* oraw, float* lse, cudaStream_t st);
 
 template <int MODE>
 int launch_attn2(const Dims& m, const MtAxialParams& p, const float* yraw, double* stats, float* coef, unsigned* cnt,
@@ -254,6 +256,13 @@ int axial_forward_launch(const Dims& m, const MtAxialParams& p, const float* x, 
   int nl = 0;
   if (mask == 0x1f) {      // accumulators + CTA-done tickets
     if (cudaMemsetAsync(saved + m.sv_stats, 0, m.sv_zero_bytes, st) != cudaSuccess) return -1;
+  }
+  // default: the whole op as ONE persistent cooperative kernel (axial_coop_fwd.cu).  MT_DEBUG_FLAGS bit5 (and the
+  // per-stage profiling entry point) keep the round-1 launch chain below, which also serves shapes it does not cover.
+  if (mask == 0x1f && !(m.dbg & 32)) {
+    const int rc = launch_coop_fwd(m, p, x, out, stats, coef, cnt, yraw, oraw, lse, st);
+    if (rc < 0) return rc;
+    if (rc > 0) { *nlaunch = rc; return 0; }
   }
   if (mask & 1) nl += launch_proj(m, p, x, yraw, stats, coef, cnt, st);
   const bool v1 = (m.dbg & 2) != 0;        // MT_DEBUG_FLAGS bit1: force the v1 (one row per thread) kernels

@@ -17,13 +17,20 @@
 #endif
 
 namespace emu {
-enum { READY = 0, WAIT_CTA = 1, WAIT_WARP = 2, DONE = 3 };
+enum { READY = 0, WAIT_CTA = 1, WAIT_WARP = 2, DONE = 3, WAIT_GRID = 4 };
 struct Fiber {
   ucontext_t ctx;
   uint3 tid;
   int lin, state;
+  int cta;                  // index into g_ctas (cooperative launches co-schedule several CTAs)
   unsigned long long slot;
   void* ts;                 // ThreadSanitizer fiber context (EMU_TSAN)
+};
+struct Cta {
+  uint3 bid;
+  unsigned char* dyn;
+  std::map<const void*, void*> blocks;      // static __shared__ storage of this CTA, by declaration
+  int first;                                // index of its first fiber
 };
 Fiber* cur = nullptr;
 uint3 g_bid = {0, 0, 0};
@@ -32,16 +39,17 @@ unsigned char* g_dyn_smem = nullptr;
 
 static ucontext_t g_sched;
 static std::vector<Fiber> g_fibers;
+static std::vector<Cta> g_ctas;
+static int g_tpc = 0;                                           // threads per CTA
 static std::vector<char*> g_stacks;
 static const std::function<void()>* g_body = nullptr;
 static const size_t STACK = 512 * 1024;
 
 const uint3& tid() { return cur->tid; }
 int lin() { return cur->lin; }
-int nthreads() { return (int)g_fibers.size(); }
-static std::map<const void*, void*> g_cta_blocks;            // static __shared__ storage of the running CTA, by declaration
+int nthreads() { return g_tpc; }
 static void* g_sched_ts = nullptr;
-static char g_sync_cta, g_sync_warp[64], g_sync_kernel[2], g_sync_cta_end;
+static char g_sync_cta, g_sync_warp[64], g_sync_kernel[2], g_sync_cta_end, g_sync_grid;
 static int g_kidx = 0;
 
 static void* fresh_block(size_t n) {                            // a NEW heap block: undefined contents, no race history
@@ -51,6 +59,7 @@ static void* fresh_block(size_t n) {                            // a NEW heap bl
   return p;
 }
 void* cta_shared(const void* key, size_t bytes) {
+  std::map<const void*, void*>& g_cta_blocks = g_ctas[cur->cta].blocks;
   auto it = g_cta_blocks.find(key);
   if (it != g_cta_blocks.end()) {
     TSAN_ONLY(__tsan_acquire(const_cast<void*>(key));)          // the allocation (by the first thread to get here) precedes every use
@@ -62,20 +71,20 @@ void* cta_shared(const void* key, size_t bytes) {
   return p;
 }
 unsigned long long exchange(unsigned long long raw, int src_lane_in_warp) {
-  const int me = cur->lin, base = me & ~31;
-  g_fibers[me].slot = raw;
+  const int f0 = g_ctas[cur->cta].first, me = cur->lin, base = me & ~31;
+  g_fibers[f0 + me].slot = raw;
   barrier_warp();
   const int src = base + (src_lane_in_warp & 31);
-  const unsigned long long r = src < (int)g_fibers.size() ? g_fibers[src].slot : raw;
+  const unsigned long long r = src < g_tpc ? g_fibers[f0 + src].slot : raw;
   barrier_warp();
   return r;
 }
 int all(int pred) {
-  const int me = cur->lin, base = me & ~31, n = (int)g_fibers.size();
-  g_fibers[me].slot = pred ? 1ull : 0ull;
+  const int f0 = g_ctas[cur->cta].first, me = cur->lin, base = me & ~31, n = g_tpc;
+  g_fibers[f0 + me].slot = pred ? 1ull : 0ull;
   barrier_warp();
   int a = 1;
-  for (int l = base; l < base + 32 && l < n; ++l) a &= (int)g_fibers[l].slot;
+  for (int l = base; l < base + 32 && l < n; ++l) a &= (int)g_fibers[f0 + l].slot;
   barrier_warp();
   return a;
 }
@@ -88,6 +97,11 @@ void barrier_cta() {
   TSAN_ONLY(__tsan_release(&g_sync_cta);)
   yield_as(WAIT_CTA);
   TSAN_ONLY(__tsan_acquire(&g_sync_cta);)
+}
+void barrier_grid() {                       // called by ONE thread per CTA (the cooperative kernels' grid barrier)
+  TSAN_ONLY(__tsan_release(&g_sync_grid);)
+  yield_as(WAIT_GRID);
+  TSAN_ONLY(__tsan_acquire(&g_sync_grid);)
 }
 void barrier_warp() {
   char* o = &g_sync_warp[(cur->lin >> 5) & 63];
@@ -106,69 +120,99 @@ static void fiber_main() {
   to_sched();
 }
 
-static void run_cta() {
-  const int n = (int)g_fibers.size();
+static void switch_in(Fiber& f) {
+  cur = &f;
+  g_bid = g_ctas[f.cta].bid;
+  g_dyn_smem = g_ctas[f.cta].dyn;
+  TSAN_ONLY(__tsan_switch_to_fiber(f.ts, __tsan_switch_to_fiber_no_sync);)
+  swapcontext(&g_sched, &f.ctx);
+}
+
+// runs the co-scheduled CTAs [0, g_ctas.size()) to completion
+static void run_ctas() {
+  const int n = g_tpc, nc = (int)g_ctas.size(), nf = (int)g_fibers.size();
   for (;;) {
     int alive = 0;
-    for (int i = 0; i < n; ++i) {
+    for (int i = 0; i < nf; ++i) {
       Fiber& f = g_fibers[i];
-      if (f.state == READY) {
-        cur = &f;
-        TSAN_ONLY(__tsan_switch_to_fiber(f.ts, __tsan_switch_to_fiber_no_sync);)
-        swapcontext(&g_sched, &f.ctx);
-      }
+      if (f.state == READY) switch_in(f);
       if (f.state != DONE) ++alive;
     }
     if (!alive) return;
     bool released = false;
     // warp barriers first: a warp whose alive lanes all wait at a warp collective continues
-    for (int w = 0; w < n; w += 32) {
-      int a = 0, ww = 0;
-      for (int l = w; l < w + 32 && l < n; ++l) { if (g_fibers[l].state != DONE) ++a; if (g_fibers[l].state == WAIT_WARP) ++ww; }
-      if (a && ww == a) { for (int l = w; l < w + 32 && l < n; ++l) if (g_fibers[l].state == WAIT_WARP) g_fibers[l].state = READY; released = true; }
+    for (int c = 0; c < nc; ++c)
+      for (int w = 0; w < n; w += 32) {
+        const int f0 = g_ctas[c].first;
+        int a = 0, ww = 0;
+        for (int l = w; l < w + 32 && l < n; ++l) { if (g_fibers[f0 + l].state != DONE) ++a; if (g_fibers[f0 + l].state == WAIT_WARP) ++ww; }
+        if (a && ww == a) { for (int l = w; l < w + 32 && l < n; ++l) if (g_fibers[f0 + l].state == WAIT_WARP) g_fibers[f0 + l].state = READY; released = true; }
+      }
+    if (released) continue;
+    for (int c = 0; c < nc; ++c) {
+      const int f0 = g_ctas[c].first;
+      int a = 0, wc = 0;
+      for (int l = 0; l < n; ++l) { if (g_fibers[f0 + l].state != DONE) ++a; if (g_fibers[f0 + l].state == WAIT_CTA) ++wc; }
+      if (a && wc == a) { for (int l = 0; l < n; ++l) g_fibers[f0 + l].state = READY; released = true; }
     }
     if (released) continue;
-    int wc = 0;
-    for (int i = 0; i < n; ++i) if (g_fibers[i].state == WAIT_CTA) ++wc;
-    if (wc == alive) { for (int i = 0; i < n; ++i) if (g_fibers[i].state == WAIT_CTA) g_fibers[i].state = READY; continue; }
-    fprintf(stderr, "emu: deadlock in CTA (%u,%u,%u): %d alive, %d at __syncthreads, rest inside a divergent warp collective\n",
-            g_bid.x, g_bid.y, g_bid.z, alive, wc);
+    // grid barrier: exactly one waiting thread in EVERY CTA of the launch, everybody else parked at a CTA barrier
+    int wg = 0, wcta = 0;
+    for (int i = 0; i < nf; ++i) { if (g_fibers[i].state == WAIT_GRID) ++wg; if (g_fibers[i].state == WAIT_CTA) ++wcta; }
+    if (wg == nc && wg + wcta == alive) {
+      for (int i = 0; i < nf; ++i) if (g_fibers[i].state == WAIT_GRID) g_fibers[i].state = READY;
+      continue;
+    }
+    fprintf(stderr, "emu: deadlock (first CTA (%u,%u,%u) of %d co-scheduled): %d alive, %d at __syncthreads, %d at the grid barrier, "
+            "rest inside a divergent warp collective or an exited CTA is missing from a grid barrier\n",
+            g_ctas[0].bid.x, g_ctas[0].bid.y, g_ctas[0].bid.z, nc, alive, wcta, wg);
     abort();
   }
 }
 
-void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
+static void launch_impl(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body, bool coop) {
   const int n = (int)(block.x * block.y * block.z);
-  g_bdim = block; g_gdim = grid; g_body = &body;
-  while ((int)g_stacks.size() < n) g_stacks.push_back((char*)aligned_alloc(64, STACK));
-  g_fibers.assign(n, Fiber());
+  const int total = (int)(grid.x * grid.y * grid.z), group = coop ? total : 1;
+  g_bdim = block; g_gdim = grid; g_body = &body; g_tpc = n;
+  while ((int)g_stacks.size() < n * group) g_stacks.push_back((char*)aligned_alloc(64, STACK));
   g_kidx ^= 1;
   TSAN_ONLY(g_sched_ts = __tsan_get_current_fiber(); __tsan_release(&g_sync_kernel[g_kidx ^ 1]);)
-  for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) {
-        g_bid = {bx, by, bz};
-        g_dyn_smem = (unsigned char*)fresh_block(smem);      // exact size: overruns are visible to AddressSanitizer
-        for (int i = 0; i < n; ++i) {
-          Fiber& f = g_fibers[i];
-          f.lin = i; f.state = READY; f.slot = 0;
-          f.tid = {(unsigned)(i % block.x), (unsigned)((i / block.x) % block.y), (unsigned)(i / (block.x * block.y))};
-          getcontext(&f.ctx);
-          f.ctx.uc_stack.ss_sp = g_stacks[i]; f.ctx.uc_stack.ss_size = STACK; f.ctx.uc_link = &g_sched;
-          makecontext(&f.ctx, fiber_main, 0);
-          TSAN_ONLY(f.ts = __tsan_create_fiber(0);)
-        }
-        run_cta();
-        TSAN_ONLY(for (int i = 0; i < n; ++i) __tsan_destroy_fiber(g_fibers[i].ts);)
-        TSAN_ONLY(__tsan_acquire(&g_sync_cta_end);)
-#ifdef EMU_TSAN
-        for (char*& st : g_stacks) { free(st); st = (char*)aligned_alloc(64, STACK); }   // stacks are reused by unrelated threads: renew
-#endif
-        free(g_dyn_smem);
-        for (auto& kv : g_cta_blocks) free(kv.second);
-        g_cta_blocks.clear();
+  for (int c0 = 0; c0 < total; c0 += group) {
+    g_ctas.assign(group, Cta());
+    g_fibers.assign((size_t)n * group, Fiber());
+    for (int c = 0; c < group; ++c) {
+      const unsigned lin = (unsigned)(c0 + c);
+      Cta& ct = g_ctas[c];
+      ct.bid = {lin % grid.x, (lin / grid.x) % grid.y, lin / (grid.x * grid.y)};
+      ct.dyn = (unsigned char*)fresh_block(smem);           // exact size: overruns are visible to AddressSanitizer
+      ct.first = c * n;
+      for (int i = 0; i < n; ++i) {
+        Fiber& f = g_fibers[c * n + i];
+        f.lin = i; f.state = READY; f.slot = 0; f.cta = c;
+        f.tid = {(unsigned)(i % block.x), (unsigned)((i / block.x) % block.y), (unsigned)(i / (block.x * block.y))};
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = g_stacks[c * n + i]; f.ctx.uc_stack.ss_size = STACK; f.ctx.uc_link = &g_sched;
+        makecontext(&f.ctx, fiber_main, 0);
+        TSAN_ONLY(f.ts = __tsan_create_fiber(0);)
       }
+    }
+    run_ctas();
+    TSAN_ONLY(for (size_t i = 0; i < g_fibers.size(); ++i) __tsan_destroy_fiber(g_fibers[i].ts);)
+    TSAN_ONLY(__tsan_acquire(&g_sync_cta_end);)
+#ifdef EMU_TSAN
+    for (char*& st : g_stacks) { free(st); st = (char*)aligned_alloc(64, STACK); }   // stacks are reused by unrelated threads: renew
+#endif
+    for (Cta& ct : g_ctas) {
+      free(ct.dyn);
+      for (auto& kv : ct.blocks) free(kv.second);
+    }
+    g_ctas.clear();
+  }
   TSAN_ONLY(__tsan_acquire(&g_sync_kernel[g_kidx]);)
   cur = nullptr; g_body = nullptr; g_dyn_smem = nullptr;
 }
+
+void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) { launch_impl(grid, block, smem, body, false); }
+// cooperative launch: ALL CTAs of the grid are co-scheduled (fibers of one OS thread), so grid barriers can complete
+void launch_coop(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) { launch_impl(grid, block, smem, body, true); }
 }  // namespace emu

@@ -42,6 +42,14 @@ static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
 static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+enum { cudaDevAttrMultiProcessorCount = 16 };
+static inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 4; return cudaSuccess; }      // a 4-"SM" device: small co-scheduled grids
+template <class F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 2; return cudaSuccess; }
+// cooperative launches of the product (axial_coop.cuh) become co-scheduled emulator launches
+#define MT_COOP_LAUNCH(kern, grid, block, smem, stream, ...) \
+  (emu::launch_coop(dim3(grid), dim3(block), (size_t)(smem), [&]() { (kern)(__VA_ARGS__); }), g_last_cuda = cudaSuccess)
+static inline long long clock64() { return 0; }
+#define __noinline__
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return cudaSuccess; }
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = nullptr; return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
@@ -59,6 +67,8 @@ int nthreads();
 void barrier_cta();
 void barrier_warp();
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+void launch_coop(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);   // all CTAs co-scheduled (grid barriers)
+void barrier_grid();                        // one thread per CTA
 void* cta_shared(const void* key, size_t bytes);   // static __shared__ storage: one fresh, poisoned heap block per CTA and declaration
 unsigned long long exchange(unsigned long long raw, int src_lane_in_warp);   // warp shuffle (all alive lanes of the warp call it)
 int all(int pred);
