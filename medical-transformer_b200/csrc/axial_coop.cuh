@@ -18,7 +18,32 @@
 
 template <> struct VecT<1> { typedef float T; };
 
+// divisor known on the host: shift when it is a power of two (every reference shape), plain division otherwise
+struct DivS { int d, lg; };
+static inline DivS make_divs(int d) {
+  DivS k; k.d = d > 0 ? d : 1; k.lg = -1;
+  for (int b = 0; b < 31; ++b) if ((1 << b) == k.d) k.lg = b;
+  return k;
+}
+// (the general case is a real call: inlined, every division site carries ~30 cold instructions, and instruction fetch is the
+//  top stall of these run-once kernels -- ncu: stalled_no_instruction 31 % of warp time)
+static __device__ __noinline__ int slow_div(int x, int d) { return x / d; }
+__device__ __forceinline__ int dv(int x, const DivS& k) { return k.lg >= 0 ? (x >> k.lg) : slow_div(x, k.d); }
+__device__ __forceinline__ int md(int x, const DivS& k) { return k.lg >= 0 ? (x & (k.d - 1)) : x - slow_div(x, k.d) * k.d; }
+
+// BN coefficients of one channel straight from the fp64 accumulators (training) or the running statistics (eval): ONE
+// out-of-line copy shared by every phase of the cooperative kernels
+static __device__ __noinline__ BnCoef coef_from_stats(const Dims& m, const double* stats, int grp, int off_sum, int off_sq, int ch,
+                                                      double inv_n, float f, const float* gamma, const float* beta,
+                                                      const float* rm, const float* rv) {
+  const bool train = m.training != 0;
+  return bn_coef(m.training, train ? stat_get(m, stats, grp, m.nstat_f, off_sum + ch) : 0.0,
+                 train ? stat_get(m, stats, grp, m.nstat_f, off_sq + ch) : 0.0, inv_n, f, gamma[ch], beta[ch],
+                 train ? 0.f : rm[ch], train ? 1.f : rv[ch], m.eps);
+}
+
 struct CoopPlan {
+  DivS dL, dL4, dLB, dKS, dHPU, dSPU, dRU, dNOCU, dPP;
   int G;                 // CTAs (all co-resident: cooperative launch)
   int SPU, HS, HPU;      // strips per unit, head split, heads per unit
   int RU, CU, NOCU;      // rows of y (q|k|v of the unit's heads), output channels, o_raw channels per unit
@@ -26,6 +51,7 @@ struct CoopPlan {
   int XP;                // SPU * L positions per unit
   int nunits, upc, nslot, resident;
   int tm, tn;            // projection GEMM thread tile
+  int tpr_q, tpr_o;      // lanes per row of the per-channel statistics passes
   int WTP;               // pitch of the transposed W slice
   // shared-memory carve (float offsets)
   int o_ca, o_cb, o_wsim, o_oa, o_ob, o_redq, o_reds, o_redo, o_tab, o_rp, o_rs, o_wt, o_x, o_slot;
@@ -56,6 +82,18 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nctas, unsi
   __syncthreads();
 }
 
+// ---- Ampere-style async copies (SASS LDGSTS): global -> shared without a register round trip, so the gathers of a unit's
+// strips overlap the table / coefficient staging that follows their issue
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
 // cooperative launch; arguments are passed as lvalues of exactly the kernel's parameter types.
 // (the CPU emulation tier of tests/emu pre-defines this macro with its own co-scheduled launch)
 #ifndef MT_COOP_LAUNCH
@@ -67,6 +105,19 @@ static inline cudaError_t coop_launch_(const void* k, dim3 g, dim3 b, size_t sme
 #define MT_COOP_LAUNCH(kern, grid, block, smem, stream, ...) \
   (g_last_cuda = coop_launch_((const void*)(kern), dim3(grid), dim3(block), (size_t)(smem), (stream), __VA_ARGS__))
 #endif
+
+// ---- developer timeline (MT_DEBUG_FLAGS bit6): thread 0 of every CTA stamps %globaltimer at the phase boundaries of the
+// cooperative kernels into a device array that mt_debug_read_phases() copies out (tools/time_ops.py --phases)
+#define MT_PH_MAX 16
+#define MT_PH_CTAS 512
+static __device__ unsigned long long g_phase_ns[MT_PH_MAX * MT_PH_CTAS];      // one copy per translation unit
+__device__ __forceinline__ void phase_stamp(const Dims& m, int ph) {
+  if ((m.dbg & 64) && threadIdx.x == 0 && blockIdx.x < MT_PH_CTAS) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_phase_ns[ph * MT_PH_CTAS + blockIdx.x] = t;
+  }
+}
 
 int coop_sm_count();
 int coop_max_ctas_env();

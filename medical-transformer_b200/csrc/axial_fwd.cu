@@ -204,7 +204,7 @@ int launch_proj(const Dims& m, const MtAxialParams& p, const float* x, float* yr
                 unsigned* cnt, cudaStream_t st);
 int launch_out(const Dims& m, const float* coef, const float* oraw, float* out, cudaStream_t st);
 int launch_coop_fwd(const Dims& m, const MtAxialParams& p, const float* x, float* out, double* stats, float* coef,
-                    unsigned* cnt, float* yraw, float* oraw, float* lse, cudaStream_t st);
+                    unsigned* cnt, float* yraw, float* oraw, float* lse, float* tabg, cudaStream_t st);
 
 template <int MODE>
 int launch_attn2(const Dims& m, const MtAxialParams& p, const float* yraw, double* stats, float* coef, unsigned* cnt,
@@ -260,7 +260,7 @@ int axial_forward_launch(const Dims& m, const MtAxialParams& p, const float* x, 
   // default: the whole op as ONE persistent cooperative kernel (axial_coop_fwd.cu).  MT_DEBUG_FLAGS bit5 (and the
   // per-stage profiling entry point) keep the round-1 launch chain below, which also serves shapes it does not cover.
   if (mask == 0x1f && !(m.dbg & 32)) {
-    const int rc = launch_coop_fwd(m, p, x, out, stats, coef, cnt, yraw, oraw, lse, st);
+    const int rc = launch_coop_fwd(m, p, x, out, stats, coef, cnt, yraw, oraw, lse, reinterpret_cast<float*>(saved + m.sv_tab), st);
     if (rc < 0) return rc;
     if (rc > 0) { *nlaunch = rc; return 0; }
   }

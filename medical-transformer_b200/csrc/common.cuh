@@ -15,7 +15,7 @@
 struct Dims {
   int N, C, H, W, axis, stride, variant, training, ngroups;
   int nrep;                // accumulator replicas in use: 8 when ngroups < 4, else 1 (groups already spread the atomics)
-  int dbg;                 // MT_DEBUG_FLAGS env (timing experiments only): bit0 = skip global statistic atomics, bit1 = force the v1 attention kernels, bit2 = skip the attention main loops, bit3 = tiled wrapped-diagonal d-relative pass, bit4 = rows / columns of k_bwd2 in separate CTAs (bits 3-4: unmeasured experiments, see axial_attn2_bwd.cu)
+  int dbg;                 // MT_DEBUG_FLAGS env (timing experiments only): bit0 = skip global statistic atomics, bit1 = force the v1 attention kernels, bit2 = skip the attention main loops, bit3 = tiled wrapped-diagonal d-relative pass, bit4 = rows / columns of k_bwd2 in separate CTAs (bits 3-4: unmeasured experiments, see axial_attn2_bwd.cu), bit5 = round-1 launch chain instead of the persistent cooperative kernels
   int L, other, B, Bg, gp, d, nt, no, LP, pos;
   float eps, momentum;
   double inv_n1, inv_n2;   // 1/(Bg*L), 1/(Bg*L*L): element counts of the BN1d / BN2d statistics
@@ -24,7 +24,7 @@ struct Dims {
   int f_qkv_sum, f_qkv_sq, f_sim_sum, f_sim_sq, f_out_sum, f_out_sq, nstat_f;
   int b_out_s1, b_out_s2, b_sim_t, b_qkv_s1, b_qkv_s2, nstat_b;
   // saved-buffer layout (byte offsets)
-  size_t sv_stats, sv_cnt, sv_coef, sv_yraw, sv_oraw, sv_lse, sv_bytes, sv_zero_bytes;
+  size_t sv_stats, sv_cnt, sv_coef, sv_yraw, sv_oraw, sv_lse, sv_tab, sv_bytes, sv_zero_bytes;
   size_t ws_bstats, ws_cnt, ws_coef, ws_gs, ws_dyh, ws_bytes, ws_zero_bytes;
   // float coefficient tables written once by the last CTA of each statistics-producing kernel
   int cf_q, cf_s, cf_o, ncoef_f;      // fwd, per group: q [2C][2] (a,b) | s [nt*G][2] (a*log2e, a) | o [no*C][2] (a,b)
@@ -77,6 +77,8 @@ static inline bool make_dims(const MtAxialDesc* d, Dims& m) {
   m.sv_yraw = off;  off = mt_align(off + sizeof(float) * (size_t)m.B * 2 * C * m.L);
   m.sv_oraw = off;  off = mt_align(off + sizeof(float) * (size_t)m.B * m.no * C * m.L);
   m.sv_lse = off;   off = mt_align(off + sizeof(float) * (size_t)m.B * MT_G * m.L);
+  // window sums of the Toeplitz tables for the closed-form similarity statistics (axial_coop_fwd.cu), built grid-wide
+  m.sv_tab = off;   off = mt_align(off + sizeof(float) * (m.pos ? (size_t)2 * (m.d + m.d * (m.d + 1) / 2) * m.L : 0));
   m.sv_bytes = off;
   off = 0;
   m.ws_bstats = off; off += sizeof(double) * (size_t)m.nrep * m.ngroups * m.nstat_b;

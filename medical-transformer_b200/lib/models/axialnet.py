@@ -364,15 +364,16 @@ class medt_net(_ShellBase):
         return self.adjust(F.relu(x))
 
     def _side_stream(self, device):
+        # module-level cache keyed by (device, current stream): nn.DataParallel rebuilds its replicas on every forward, so
+        # a per-instance cache would create (and destroy) a stream per replica and iteration
         if os.environ.get("MEDT_NO_BRANCH_STREAM"):
             return None
-        st = getattr(self, "_streams", None)
+        dev = torch.device(device)
+        key = ("local", dev.index, torch.cuda.current_stream(dev).cuda_stream)
+        st = _FORK_STREAMS.get(key)
         if st is None:
-            st = self._streams = {}
-        key = torch.device(device).index
-        if key not in st:
-            st[key] = torch.cuda.Stream(device=device)
-        return st[key]
+            st = _FORK_STREAMS[key] = torch.cuda.Stream(device=dev)
+        return st
 
     def forward(self, x):
         return self._forward_impl(x)

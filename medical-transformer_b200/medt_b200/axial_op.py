@@ -116,9 +116,11 @@ def axial_attention(x, mod, ngroups: int = 1):
         raise RuntimeError(f"axial length {L} does not match kernel_size {mod.kernel_size} of the position table")
     gated = variant == "gated"
     bq, bs, bo = mod.bn_qkv, mod.bn_similarity, mod.bn_output
+    from .shell_ops import check_bn
+    for bn in (bq, bs, bo):
+        check_bn(bn)
     training = mod.training
-    cfg = (1 if mod.width else 0, int(mod.stride), variant, bool(training), int(ngroups), float(bq.eps),
-           float(bq.momentum if bq.momentum is not None else 0.1))
+    cfg = (1 if mod.width else 0, int(mod.stride), variant, bool(training), int(ngroups), float(bq.eps), float(bq.momentum))
     out = AxialAttnFunction.apply(
         x, mod.qkv_transform.weight, getattr(mod, "relative", None),
         mod.f_qr if gated else None, mod.f_kr if gated else None, mod.f_sv if gated else None,

@@ -120,12 +120,22 @@ class BnAct(torch.autograd.Function):
         return (dx if need[0] else None, dres, dg if need[2] else None, db if need[3] else None, None, None, None)
 
 
+def check_bn(bn):
+    """The kernels implement the reference's BatchNorm configuration only (affine, running statistics, exponential
+    momentum); anything else raises instead of being silently approximated."""
+    if bn.momentum is None:
+        raise NotImplementedError("medt_b200: BatchNorm(momentum=None) (cumulative average) is not implemented by the kernels")
+    if not bn.affine or not bn.track_running_stats or bn.running_mean is None:
+        raise NotImplementedError("medt_b200: the kernels need affine BatchNorm with track_running_stats=True")
+
+
 def bn_act(x, bn, groups: int = 1, relu: bool = True, residual=None):
     """[relu](bn(x) [+ residual]); `bn` is the module's own nn.BatchNorm2d (parameters, running
     statistics and num_batches_tracked are updated exactly as `groups` successive calls would)."""
+    check_bn(bn)
     training = bn.training
     g = groups if training else 1
-    cfg = (int(g), bool(training), bool(relu), float(bn.eps), float(bn.momentum if bn.momentum is not None else 0.1))
+    cfg = (int(g), bool(training), bool(relu), float(bn.eps), float(bn.momentum))
     y = BnAct.apply(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, cfg)
     if training:
         if getattr(bn, "_nbt_deferred", False):

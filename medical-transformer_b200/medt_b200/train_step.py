@@ -126,14 +126,14 @@ class TrainStep:
         self.loss = torch.zeros((), device=self.device)
         self.loss_pin = torch.zeros(loss_slots).pin_memory()
         self._slot = 0
+        self._stage_ev = None
         self.graph = None
         self.opt = None
         self.steps_done = 0
-        # default: flat mode on one GPU; with world_size > 1 the per-parameter optimizer + FlatBucket path (the one
-        # measured on 2 and 4 B200s this round) stays the default until the flat path has run under NCCL -- its host
-        # logic is covered on CPU by tests/test_ddp_gloo.py; pass flat_adam=True to use it.
+        # default: flat mode (one fused-Adam launch on one tensor; the flat gradient is also the NCCL bucket), on one GPU and
+        # under NCCL alike.  flat_adam=False / MEDT_NO_FLAT_ADAM=1 keeps the per-parameter optimizer + FlatBucket path.
         if flat_adam is None:
-            flat_adam = self.world == 1 and not os.environ.get("MEDT_NO_FLAT_ADAM")
+            flat_adam = not os.environ.get("MEDT_NO_FLAT_ADAM")
         self.flat_adam = bool(flat_adam)
         self.groups = []
         self._build()
@@ -189,37 +189,35 @@ class TrainStep:
             self._build_flat()
             return
         self.bucket = FlatBucket(self.active, self.pg) if self.world > 1 else None
-        old_state = self.opt.state_dict() if self.opt is not None else None
+        # Adam state that already exists (a recapture after the epoch-10 un-freeze, train.py:169-171, or an lr change) is
+        # kept PER PARAMETER: the reference's optimizer holds every parameter from the start (train.py:111), so moments and
+        # step counts of the old parameters continue and only the newly active ones start at step 1
+        snap = {}
+        if self.opt is not None:
+            for q, st in self.opt.state.items():
+                snap[id(q)] = {k: v.clone() for k, v in st.items() if torch.is_tensor(v)}
         self.opt = self._adam(self.active)
-        if old_state is not None and len(old_state["param_groups"][0]["params"]) == len(self.active):
-            self.opt.load_state_dict(old_state)
-        if self.use_graph:
-            side = torch.cuda.Stream(device=self.device)
-            side.wait_stream(torch.cuda.current_stream(self.device))
-            state = {k: v.clone() for k, v in self.model.state_dict().items()}
-            with torch.cuda.stream(side):           # warm-up (allocator, cuDNN autotune, lazy init)
-                for _ in range(3):
-                    self._step_body()
-            torch.cuda.current_stream(self.device).wait_stream(side)
-            torch.cuda.synchronize(self.device)
-            # undo the warm-up's parameter / statistic / optimizer updates
-            self.model.load_state_dict(state)
-            self.opt = self._adam(self.active)
-            if old_state is not None and len(old_state["param_groups"][0]["params"]) == len(self.active):
-                self.opt.load_state_dict(old_state)
-            # one more eager step on the fresh optimizer so its state tensors exist before capture
-            self._step_body()
-            self.model.load_state_dict(state)
-            for st in self.opt.state.values():
-                for v in st.values():
+        state = {k: v.clone() for k, v in self.model.state_dict().items()}
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):               # warm-up (allocator, cuDNN autotune, lazy init); creates the state tensors
+            for _ in range(3 if self.use_graph else 1):
+                self._step_body()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.model.load_state_dict(state)           # undo the warm-up's parameter / statistic updates
+        with torch.no_grad():
+            for q in self.active:
+                for k, v in self.opt.state[q].items():
                     if torch.is_tensor(v):
-                        v.zero_()
-            torch.cuda.synchronize(self.device)
+                        old = snap.get(id(q), {}).get(k)
+                        v.zero_() if old is None else v.copy_(old)
+        torch.cuda.synchronize(self.device)
+        if self.use_graph:
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self._step_body()
-            torch.cuda.synchronize(self.device)
-            # capture does not execute: state is still the restored one
+            torch.cuda.synchronize(self.device)     # capture does not execute: state is still the restored one
 
     def _build_flat(self):
         self.bucket = None
@@ -285,17 +283,32 @@ class TrainStep:
 
     def step(self, x_host, y_host):
         """End-to-end step from host tensors.  Returns the slot of `loss_pin` that will hold this
-        step's loss once the stream has drained (no host sync here)."""
+        step's loss once the stream has drained (no host sync here unless the inputs are pageable: then the staging
+        buffer of the previous step must have been consumed before it is overwritten).
+        The captured step has a fixed batch shape: a ragged last batch raises (use DataLoader(drop_last=True))."""
+        if tuple(x_host.shape) != tuple(self.x.shape) or tuple(y_host.shape) != tuple(self.y.shape):
+            raise ValueError(f"TrainStep was captured for x {tuple(self.x.shape)} / y {tuple(self.y.shape)}, got "
+                             f"{tuple(x_host.shape)} / {tuple(y_host.shape)} (copy_ would silently broadcast)")
+        staged = False
+        if not (x_host.is_pinned() and y_host.is_pinned()):
+            if self._stage_ev is not None:
+                self._stage_ev.synchronize()        # the previous step's DMA out of x_pin / y_pin has finished
         if x_host.is_pinned():
             self.x.copy_(x_host, non_blocking=True)
         else:
             self.x_pin.copy_(x_host)
             self.x.copy_(self.x_pin, non_blocking=True)
+            staged = True
         if y_host.is_pinned():
             self.y.copy_(y_host, non_blocking=True)
         else:
             self.y_pin.copy_(y_host)
             self.y.copy_(self.y_pin, non_blocking=True)
+            staged = True
+        if staged:
+            if self._stage_ev is None:
+                self._stage_ev = torch.cuda.Event()
+            self._stage_ev.record(torch.cuda.current_stream(self.device))
         self.step_resident()
         slot = self._slot
         self.loss_pin[slot:slot + 1].copy_(self.loss.reshape(1), non_blocking=True)

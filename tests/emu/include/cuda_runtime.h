@@ -49,6 +49,7 @@ template <class F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMult
 #define MT_COOP_LAUNCH(kern, grid, block, smem, stream, ...) \
   (emu::launch_coop(dim3(grid), dim3(block), (size_t)(smem), [&]() { (kern)(__VA_ARGS__); }), g_last_cuda = cudaSuccess)
 static inline long long clock64() { return 0; }
+template <class T> static inline cudaError_t cudaMemcpyFromSymbol(void* dst, const T& sym, size_t n) { memcpy(dst, &sym, n); return cudaSuccess; }
 #define __noinline__
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return cudaSuccess; }
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = nullptr; return cudaSuccess; }

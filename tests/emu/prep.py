@@ -19,6 +19,10 @@ BODIES = {
     r"void\s+tma_strips_issue\s*\(\s*uint64_t\s*\*\s*bar\s*,\s*float\s*\*\s*dst\s*,\s*const\s+float\s*\*\s*src\s*,\s*uint32_t\s+bytes\s*\)":
         "(void)bar; memcpy(dst, src, bytes);",
     r"void\s+tma_strips_wait\s*\(\s*uint64_t\s*\*\s*bar\s*\)": "(void)bar;",
+    r"void\s+phase_stamp\s*\(\s*const\s+Dims\s*&\s*m\s*,\s*int\s+ph\s*\)": "(void)m; (void)ph;",
+    r"void\s+cp_async4\s*\(\s*float\s*\*\s*dst_smem\s*,\s*const\s+float\s*\*\s*src\s*\)": "*dst_smem = *src;",
+    r"void\s+cp_async16\s*\(\s*float\s*\*\s*dst_smem\s*,\s*const\s+float\s*\*\s*src\s*\)": "memcpy(dst_smem, src, 16);",
+    r"void\s+cp_async_wait_all\s*\(\s*\)": "",
     # grid barrier of the cooperative kernels: CTA barrier, one thread parks at the scheduler's grid barrier, CTA barrier
     r"void\s+grid_barrier\s*\(\s*unsigned\s*\*\s*bar\s*,\s*unsigned\s+nctas\s*,\s*unsigned\s*&\s*epoch\s*\)":
         "(void)bar; (void)nctas; ++epoch; __syncthreads(); if (threadIdx.x == 0) emu::barrier_grid(); __syncthreads();",
