@@ -375,6 +375,11 @@ int launch_bwd_gather(const Dims& m, const MtAxialParams& p, const float* dout, 
                       const double* stats, double* bstats, float* bcoef, unsigned* bcnt, cudaStream_t st);
 int launch_bwd_proj(const Dims& m, const MtAxialParams& p, const MtAxialGrads& gr, const float* x, const float* bcoef,
                     const float* yraw, const float* dyh, cudaStream_t st);
+int launch_bwd_dw(const Dims& m, const MtAxialGrads& gr, const float* x, const float* bcoef, const float* yraw,
+                  const float* dyh, cudaStream_t st);
+int launch_coop_bwd(const Dims& m, const MtAxialParams& p, const MtAxialGrads& gr, const float* x, const float* dout,
+                    const double* stats, const float* coef, const float* yraw, const float* oraw, const float* lse,
+                    double* bstats, float* bcoef, unsigned* bcnt, float* dyh, cudaStream_t st);
 static int pow2_le(int x) { int p = 1; while (p * 2 <= x) p *= 2; return p; }
 
 template <typename K>
@@ -406,6 +411,19 @@ int axial_backward_launch(const Dims& m, const MtAxialParams& p, const float* x,
   float* gs = reinterpret_cast<float*>(ws + m.ws_gs);
   float* dyh = reinterpret_cast<float*>(ws + m.ws_dyh);
   int nl = 0;
+  // default: ONE persistent cooperative kernel (axial_coop_bwd.cu) + the weight-gradient GEMM on the side stream.
+  // MT_DEBUG_FLAGS bit5, the per-stage profiling entry point and shapes it does not cover use the launch chain below.
+  if (mask == 0x1f && !(m.dbg & 32)) {
+    if (m.pos && !gr.drelative) return -3;
+    if (cudaMemsetAsync(ws + m.ws_bstats, 0, m.ws_zero_bytes, st) != cudaSuccess) return -1;
+    const int rc = launch_coop_bwd(m, p, gr, x, dout, stats, coef, yraw, oraw, lse, bstats, bcoef, bcnt, dyh, st);
+    if (rc < 0) return -1;
+    if (rc > 0) {
+      *nlaunch = rc + launch_bwd_dw(m, gr, x, bcoef, yraw, dyh, st);
+      g_last_cuda = cudaGetLastError();
+      return g_last_cuda == cudaSuccess ? 0 : -1;
+    }
+  }
   if (mask == 0x1f) {
   if (cudaMemsetAsync(ws + m.ws_bstats, 0, m.ws_zero_bytes, st) != cudaSuccess) return -1;
   if (m.pos && gr.drelative &&

@@ -27,13 +27,13 @@ static inline DivS make_divs(int d) {
 }
 // (the general case is a real call: inlined, every division site carries ~30 cold instructions, and instruction fetch is the
 //  top stall of these run-once kernels -- ncu: stalled_no_instruction 31 % of warp time)
-static __device__ __noinline__ int slow_div(int x, int d) { return x / d; }
-__device__ __forceinline__ int dv(int x, const DivS& k) { return k.lg >= 0 ? (x >> k.lg) : slow_div(x, k.d); }
-__device__ __forceinline__ int md(int x, const DivS& k) { return k.lg >= 0 ? (x & (k.d - 1)) : x - slow_div(x, k.d) * k.d; }
+__device__ __forceinline__ int slow_div(int x, int d) { return x / d; }
+__device__ __forceinline__ int dv(int x, const DivS k) { return k.lg >= 0 ? (x >> k.lg) : slow_div(x, k.d); }
+__device__ __forceinline__ int md(int x, const DivS k) { return k.lg >= 0 ? (x & (k.d - 1)) : x - slow_div(x, k.d) * k.d; }
 
 // BN coefficients of one channel straight from the fp64 accumulators (training) or the running statistics (eval): ONE
 // out-of-line copy shared by every phase of the cooperative kernels
-static __device__ __noinline__ BnCoef coef_from_stats(const Dims& m, const double* stats, int grp, int off_sum, int off_sq, int ch,
+__device__ __forceinline__ BnCoef coef_from_stats(const Dims& m, const double* stats, int grp, int off_sum, int off_sq, int ch,
                                                       double inv_n, float f, const float* gamma, const float* beta,
                                                       const float* rm, const float* rv) {
   const bool train = m.training != 0;
@@ -49,7 +49,7 @@ struct CoopPlan {
   int RU, CU, NOCU;      // rows of y (q|k|v of the unit's heads), output channels, o_raw channels per unit
   int RT, KS, LB;        // rows per thread, key split (lanes sharing a row block), L / RT
   int XP;                // SPU * L positions per unit
-  int nunits, upc, nslot, resident;
+  int nunits, upc, nslot, resident, contig;
   int tm, tn;            // projection GEMM thread tile
   int tpr_q, tpr_o;      // lanes per row of the per-channel statistics passes
   int WTP;               // pitch of the transposed W slice

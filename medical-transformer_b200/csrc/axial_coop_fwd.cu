@@ -29,7 +29,7 @@ __device__ __forceinline__ float warp_sum(float v) { return seg_sum(v, 32); }
 // moments the caller just derived (c.mean / c.var of the RAW value; f = gate in front of the BN).  Several groups: the
 // sequential chain of `ngroups` BatchNorm calls, with the groups' moments loaded eight at a time (one L2 round trip per
 // batch instead of one per group).
-__device__ __noinline__ void ema_apply(const Dims& m, float* rm, float* rv, int ch, const BnCoef& c, const double* stats,
+__device__ __forceinline__ void ema_apply(const Dims& m, float* rm, float* rv, int ch, const BnCoef& c, const double* stats,
                                        int off_sum, int off_sq, double inv_n, float unbias, float f) {
   const float mom = m.momentum;
   float m_ = rm[ch], v_ = rv[ch];
@@ -119,7 +119,7 @@ __device__ __forceinline__ void rows_stats(const float* __restrict__ blk, int nr
 }
 
 // y = a[row] * y + b[row] in place on a [nstrips][RU][L] block
-__device__ __forceinline__ void normalise_rows(float* __restrict__ Ys, int total, int L, const DivS& dL4, const DivS& dRU,
+__device__ __forceinline__ void normalise_rows(float* __restrict__ Ys, int total, int L, const DivS dL4, const DivS dRU,
                                                const float* __restrict__ ca, const float* __restrict__ cb) {
   if ((L & 3) == 0) {
     float4* y4 = reinterpret_cast<float4*>(Ys);
@@ -199,7 +199,8 @@ k_axial_fwd(Dims m, MtAxialParams p, CoopPlan pl, const float* __restrict__ x, f
   };
 
   // ---------------------------------------------------------------- one-time staging
-  if (cta < pl.nunits) issue_x((cta / HS) * SPU);                 // first unit's gather is in flight during everything below
+  { const int u0 = pl.contig ? cta * pl.upc : cta;                // first unit's gather is in flight during everything below
+    if (u0 < pl.nunits) issue_x((u0 / HS) * SPU); }
   for (int idx = tid; idx < RU * C; idx += blockDim.x) {
     const int r = idx / C, k = idx - r * C;
     cp_async4(Wt + k * pl.WTP + r, p.w_qkv + (size_t)(row0 + r) * C + k);
@@ -238,7 +239,7 @@ k_axial_fwd(Dims m, MtAxialParams p, CoopPlan pl, const float* __restrict__ x, f
   {
     int cur = -1;
     for (int k = 0; k < pl.upc; ++k) {
-      const int u = cta + k * G;
+      const int u = pl.contig ? cta * pl.upc + k : cta + k * G;
       if (u >= pl.nunits) break;
       const int b0 = (u / HS) * SPU, grp = b0 / m.Bg;
       float* Ys = slots + (size_t)(pl.resident ? k : 0) * pl.slot_fl;
@@ -301,7 +302,7 @@ k_axial_fwd(Dims m, MtAxialParams p, CoopPlan pl, const float* __restrict__ x, f
     if (POS) for (int i = tid; i < pl.tab_fl; i += blockDim.x) tab[i] = __ldcg(tabg + i);
     int cur = -1;
     for (int k = 0; k < pl.upc; ++k) {
-      const int u = cta + k * G;
+      const int u = pl.contig ? cta * pl.upc + k : cta + k * G;
       if (u >= pl.nunits) break;
       const int b0 = (u / HS) * SPU, grp = b0 / m.Bg;
       float* Ys = slots + (size_t)(pl.resident ? k : 0) * pl.slot_fl;
@@ -404,7 +405,7 @@ k_axial_fwd(Dims m, MtAxialParams p, CoopPlan pl, const float* __restrict__ x, f
   {
     int cur = -1;
     for (int k = 0; k < pl.upc; ++k) {
-      const int u = cta + k * G;
+      const int u = pl.contig ? cta * pl.upc + k : cta + k * G;
       if (u >= pl.nunits) break;
       const int b0 = (u / HS) * SPU, grp = b0 / m.Bg;
       float* Ys = slots + (size_t)(pl.resident ? k : 0) * pl.slot_fl;
@@ -595,7 +596,7 @@ k_axial_fwd(Dims m, MtAxialParams p, CoopPlan pl, const float* __restrict__ x, f
     const float invp = 1.f / (float)(st_ * st_);
     int cur = -1;
     for (int k = 0; k < pl.upc; ++k) {
-      const int u = cta + k * G;
+      const int u = pl.contig ? cta * pl.upc + k : cta + k * G;
       if (u >= pl.nunits) break;
       const int b0 = (u / HS) * SPU, grp = b0 / m.Bg;
       float* Os = slots + (size_t)(pl.resident ? k : 0) * pl.slot_fl + pl.ys_fl;
@@ -703,7 +704,7 @@ int coop_rows_tpr(int nrows, int L) {
 }
 
 // fills `pl` for a grid of at most `maxctas` CTAs; returns false when one unit does not fit in shared memory
-static bool coop_plan_fwd(const Dims& m, int maxctas, size_t smem_cap, CoopPlan& pl) {
+static bool coop_plan_fwd_hs(const Dims& m, int maxctas, size_t smem_cap, CoopPlan& pl, int hs_min) {
   const int C = m.C, L = m.L, D = m.d, GP = 2 * D, NO = m.no;
   pl.RT = coop_rt(m);
   pl.LB = L / pl.RT;
@@ -712,6 +713,7 @@ static bool coop_plan_fwd(const Dims& m, int maxctas, size_t smem_cap, CoopPlan&
   const int nsb = m.B / pl.SPU;
   int hs = 1;
   while (hs < MT_G && nsb * hs * 2 <= maxctas) hs *= 2;  // split heads while that still adds CTAs
+  if (hs < hs_min) hs = hs_min;                          // smaller units when one does not fit in shared memory
   static const int force_hs = coop_env_int("MT_COOP_HS");
   if (force_hs == 1 || force_hs == 2 || force_hs == 4 || force_hs == 8) hs = force_hs;
   pl.HS = hs; pl.HPU = MT_G / hs;
@@ -721,8 +723,10 @@ static bool coop_plan_fwd(const Dims& m, int maxctas, size_t smem_cap, CoopPlan&
   int G = pl.nunits < maxctas ? pl.nunits : maxctas;
   G -= G % hs;
   if (G < hs) return false;
-  pl.G = G;
   pl.upc = (pl.nunits + G - 1) / G;
+  pl.contig = (hs == 1 && pl.upc > 1) ? 1 : 0;          // consecutive strips share a statistic group: fewer coefficient reloads
+  if (pl.contig) G = (pl.nunits + pl.upc - 1) / pl.upc;
+  pl.G = G;
   // key split: aim at >= 256 (row block, key range) items per unit, at most 8 lanes per row block
   int ks = 1;
   const int items0 = pl.SPU * pl.HPU * pl.LB;
@@ -767,6 +771,12 @@ static bool coop_plan_fwd(const Dims& m, int maxctas, size_t smem_cap, CoopPlan&
   return true;
 }
 
+static bool coop_plan_fwd(const Dims& m, int maxctas, size_t smem_cap, CoopPlan& pl) {
+  for (int hs = 1; hs <= MT_G; hs *= 2)
+    if (coop_plan_fwd_hs(m, maxctas, smem_cap, pl, hs)) return true;
+  return false;
+}
+
 template <int D, bool POS, int RT>
 static int coop_launch_fwd(const Dims& m, const MtAxialParams& p, const float* x, float* out, double* stats, float* coef,
                            unsigned* cnt, float* yraw, float* oraw, float* lse, float* tabg, cudaStream_t st) {
@@ -799,7 +809,7 @@ static int coop_launch_fwd(const Dims& m, const MtAxialParams& p, const float* x
       if (nb >= 2) ok = true;
     } else ok = true;
   }
-  if (!ok) return -2;
+  if (!ok) return 0;              // not covered (one unit does not fit): the caller falls back to the launch chain
   Dims mm = m; MtAxialParams pp = p;
   MT_COOP_LAUNCH((kern), pl.G, MT_COOP_THREADS, pl.smem_bytes, st, mm, pp, pl, x, out, stats, coef, cnt, yraw, oraw, lse, tabg);
   return g_last_cuda == cudaSuccess ? 1 : -1;

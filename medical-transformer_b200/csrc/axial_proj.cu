@@ -347,3 +347,24 @@ int launch_bwd_proj(const Dims& m, const MtAxialParams& p, const MtAxialGrads& g
   mt_side_join(st, sd);
   return 2;
 }
+
+// weight gradient only (the cooperative backward kernel produces dX itself): dW = dY_raw X^T on the forked side stream
+int launch_bwd_dw(const Dims& m, const MtAxialGrads& gr, const float* x, const float* bcoef, const float* yraw,
+                  const float* dyh, cudaStream_t st) {
+  if (!gr.dw_qkv) return 0;
+  int TS, TL, nTL, nTS;
+  proj_tiling(m, TS, TL, nTL, nTS);
+  const int ntiles = m.ngroups * nTS * nTL;
+  cudaStream_t sd = mt_side_fork(st);
+  const int mn = ((2 * m.C + 63) / 64) * ((m.C + 63) / 64);
+  int ksplit = (148 + mn - 1) / mn;
+  if (ksplit > ntiles) ksplit = ntiles;
+  dim3 grid((2 * m.C + 63) / 64, (m.C + 63) / 64, ksplit);
+  const size_t smem = sizeof(float) * (2 * 64 * TILE_LD + 6 * (size_t)m.C);
+  static bool once = (cudaFuncSetAttribute(k_bwd_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), true);
+  (void)once;
+  cudaMemsetAsync(gr.dw_qkv, 0, sizeof(float) * 2 * (size_t)m.C * m.C, sd);
+  k_bwd_dw<<<grid, 256, smem, sd>>>(m, gr, x, bcoef, yraw, dyh, TS, TL, nTS * nTL, nTL, ntiles);
+  mt_side_join(st, sd);
+  return 1;
+}

@@ -396,6 +396,75 @@ __device__ __forceinline__ void bwd_param_grads(const Dims& m, const MtAxialPara
   }
 }
 
+// Grid-distributed form of bwd_param_grads for the cooperative backward kernel: item k of [0, 2C + NO*C + NT*8) is one
+// BN channel; thread `first`, `first + stride`, ... of the whole grid take the items, the four gate gradients are summed
+// with atomics into gr.dgates (zeroed by the kernel before its first barrier).
+__device__ __forceinline__ void bwd_param_grads_dist(const Dims& m, const MtAxialParams& p, const MtAxialGrads& gr,
+                                                     const double* stats, const double* bstats, int first, int stride) {
+  const int C = m.C, NO = m.no, NOC = NO * C, NT = m.nt, nitems = 2 * C + NOC + NT * MT_G;
+  for (int item = first; item < nitems; item += stride) {
+    if (item < 2 * C) {
+      const int ch = item;
+      float dg = 0.f, db = 0.f;
+      for (int g = 0; g < m.ngroups; ++g) {
+        const double s1 = stat_get(m, bstats, g, m.nstat_b, m.b_qkv_s1 + ch), s2 = stat_get(m, bstats, g, m.nstat_b, m.b_qkv_s2 + ch);
+        if (m.training) {
+          Moments mo = moments(stat_get(m, stats, g, m.nstat_f, m.f_qkv_sum + ch), stat_get(m, stats, g, m.nstat_f, m.f_qkv_sq + ch), m.inv_n1);
+          dg += (float)fma(-mo.mu_d, s1, s2) * rsqrt_nr(mo.var + m.eps);
+        } else {
+          dg += (float)fma(-(double)p.bn_qkv_rm[ch], s1, s2) * rsqrt_nr(p.bn_qkv_rv[ch] + m.eps);
+        }
+        db += (float)s1;
+      }
+      if (gr.dbn_qkv_w) gr.dbn_qkv_w[ch] = dg;
+      if (gr.dbn_qkv_b) gr.dbn_qkv_b[ch] = db;
+    } else if (item < 2 * C + NOC) {
+      const int ch = item - 2 * C, sidx = NO == 2 ? (ch & 1) : 0;
+      const float f = sidx ? gate_val(p.f_sve) : gate_val(p.f_sv);
+      const float gam = p.bn_out_w[ch];
+      float dg = 0.f, db = 0.f, gp_ = 0.f;
+      for (int g = 0; g < m.ngroups; ++g) {
+        const double s1 = stat_get(m, bstats, g, m.nstat_b, m.b_out_s1 + ch / NO), s2 = stat_get(m, bstats, g, m.nstat_b, m.b_out_s2 + ch);
+        if (m.training) {
+          Moments mo = moments(stat_get(m, stats, g, m.nstat_f, m.f_out_sum + ch), stat_get(m, stats, g, m.nstat_f, m.f_out_sq + ch), m.inv_n1);
+          const float inv = rsqrt_nr(f * f * mo.var + m.eps), d = (float)fma(-mo.mu_d, s1, s2);
+          dg += f * d * inv;
+          gp_ += gam * d * m.eps * inv * inv * inv;
+        } else {
+          const float inv = rsqrt_nr(p.bn_out_rv[ch] + m.eps);
+          dg += (f * (float)s2 - p.bn_out_rm[ch] * (float)s1) * inv;
+          gp_ += gam * inv * (float)s2;
+        }
+        db += (float)s1;
+      }
+      if (gr.dbn_out_w) gr.dbn_out_w[ch] = dg;
+      if (gr.dbn_out_b) gr.dbn_out_b[ch] = db;
+      if (gr.dgates) atomicAdd(gr.dgates + 2 + sidx, gp_);
+    } else {
+      const int ch = item - 2 * C - NOC, t = ch / MT_G;
+      const float f = t == 0 ? 1.f : (t == 1 ? gate_val(p.f_qr) : gate_val(p.f_kr));
+      const float gam = p.bn_sim_w[ch];
+      float dg = 0.f, gp_ = 0.f;
+      for (int g = 0; g < m.ngroups; ++g) {
+        const float T = (float)stat_get(m, bstats, g, m.nstat_b, m.b_sim_t + ch);
+        if (m.training) {
+          Moments mo = moments(stat_get(m, stats, g, m.nstat_f, m.f_sim_sum + ch), stat_get(m, stats, g, m.nstat_f, m.f_sim_sq + ch), m.inv_n2);
+          const float inv = rsqrt_nr(f * f * mo.var + m.eps);
+          dg += f * T * inv;
+          gp_ += gam * T * m.eps * inv * inv * inv;
+        } else {
+          const float inv = rsqrt_nr(p.bn_sim_rv[ch] + m.eps);
+          dg += f * T * inv;
+          gp_ += gam * inv * T;
+        }
+      }
+      if (gr.dbn_sim_w) gr.dbn_sim_w[ch] = dg;
+      if (gr.dbn_sim_b) gr.dbn_sim_b[ch] = 0.f;        // sum dZ == 0: softmax is shift invariant
+      if (t > 0 && gr.dgates) atomicAdd(gr.dgates + (t - 1), gp_);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Batched staging.  ncu (profiles/r1_notes.md): the first kernels spent most of their cycles in
 // "long scoreboard" stalls because global->shared staging loops did load -> use -> store one

@@ -100,19 +100,22 @@ def time_op(lib_, dev, flush, variant, C, N, H, W, axis, stride, ngroups, reps):
         for _ in range(2):
             graph.replay()
         res[name + "_us_graph"] = round(bench.timed_steps(graph.replay, reps, lambda: None, dev) / reps / 10 * 1e3, 2)
-        if name == "fwd" and os.environ.get("MT_DEBUG_FLAGS") and int(os.environ["MT_DEBUG_FLAGS"]) & 64:
+        if os.environ.get("MT_DEBUG_FLAGS") and int(os.environ["MT_DEBUG_FLAGS"]) & 64:
             import numpy as np
             torch.cuda.synchronize(dev)
             fn()
             torch.cuda.synchronize(dev)
             buf = (ctypes.c_ulonglong * (16 * 512))()
-            lib_.mt_debug_read_phases(buf, 16 * 512)
+            (lib_.mt_debug_read_phases if name == "fwd" else lib_.mt_debug_read_phases_bwd)(buf, 16 * 512)
             a = np.frombuffer(buf, dtype=np.uint64).reshape(16, 512).astype(np.int64)
-            n = int((a[0] > 0).sum())
-            t0 = a[0, :n].min()
-            res["phases_us_max_over_ctas"] = [round(float((a[k, :n].max() - t0) / 1e3), 2) for k in range(10)]
-            res["phases_us_min_over_ctas"] = [round(float((a[k, :n].min() - t0) / 1e3), 2) for k in range(10)]
-            res["phase_ctas"] = n
+            t0 = a[0][a[0] > 0].max() - 200000           # stamps of this launch: within 200 us of the newest start stamp
+            sel = a[0] >= t0
+            n = int(sel.sum())
+            t0 = a[0][sel].min()
+            pre = "" if name == "fwd" else "bwd_"
+            res[pre + "phases_us_max_over_ctas"] = [round(float((a[k][sel].max() - t0) / 1e3), 2) for k in range(10)]
+            res[pre + "phases_us_min_over_ctas"] = [round(float((a[k][sel].min() - t0) / 1e3), 2) for k in range(10)]
+            res[pre + "phase_ctas"] = n
     B = N * (W if axis == 0 else H)
     res["alg_mb_fwd"] = round(2 * B * C * L * 4 / 1e6, 3)
     res["exp_G_per_s_fwd_warm"] = round(8 * B * L * L / (res["fwd_us_warm"] * 1e-6) / 1e9, 1)
