@@ -87,7 +87,7 @@ __device__ __forceinline__ BnBwdCoef bwd_coef_from_stats(const Dims& m, const do
 }  // namespace
 
 template <int D, bool POS, int RT>
-__global__ void __launch_bounds__(MT_COOP_THREADS)
+__global__ void __launch_bounds__(MT_COOP_THREADS, (D <= 2 ? 2 : 1))
 k_axial_bwd(Dims m, MtAxialParams p, MtAxialGrads gr, CoopPlanB pl, const float* __restrict__ x, const float* __restrict__ dout,
             const double* __restrict__ stats, const float* __restrict__ coef, const float* __restrict__ yraw,
             const float* __restrict__ oraw, const float* __restrict__ lse, double* __restrict__ bstats,
@@ -782,13 +782,21 @@ extern "C" int mt_debug_read_phases_bwd(unsigned long long* host, int n) {
 
 // =============================================================================================== host side
 int coop_rt(const Dims& m);
+// RT of the backward kernel: d = 1 runs RT = 2 (113 registers, two CTAs per SM; measured 13 % faster than RT = 4 at one
+// CTA per SM on the L = 64 layers); MT_BWD_RT=4 restores the forward's choice for A/B runs
+static int coop_rt_bwd(const Dims& m) {
+  int rt = coop_rt(m);
+  static const int force = getenv("MT_BWD_RT") ? atoi(getenv("MT_BWD_RT")) : 0;
+  if (m.d == 1 && rt == 4 && force != 4) rt = 2;
+  return rt;
+}
 int coop_force_stream();
 int coop_env_int(const char* name);
 int coop_rows_tpr(int nrows, int L);
 
 static bool coop_plan_bwd_hs(const Dims& m, int maxctas, size_t smem_cap, CoopPlanB& pl, int hs_min) {
   const int C = m.C, L = m.L, D = m.d, GP = 2 * D, NO = m.no;
-  pl.RT = coop_rt(m);
+  pl.RT = coop_rt_bwd(m);
   pl.LB = L / pl.RT;
   pl.SPU = m.stride;
   if (m.other % pl.SPU) return false;
@@ -910,7 +918,7 @@ static int coop_launch_bwd(const Dims& m, const MtAxialParams& p, const MtAxialG
 int launch_coop_bwd(const Dims& m, const MtAxialParams& p, const MtAxialGrads& gr, const float* x, const float* dout,
                     const double* stats, const float* coef, const float* yraw, const float* oraw, const float* lse,
                     double* bstats, float* bcoef, unsigned* bcnt, float* dyh, cudaStream_t st) {
-  const int rt = coop_rt(m);
+  const int rt = coop_rt_bwd(m);
 #define GO(DD, RR)                                                                                                          \
   return m.pos ? coop_launch_bwd<DD, true, RR>(m, p, gr, x, dout, stats, coef, yraw, oraw, lse, bstats, bcoef, bcnt, dyh, st)   \
                : coop_launch_bwd<DD, false, RR>(m, p, gr, x, dout, stats, coef, yraw, oraw, lse, bstats, bcoef, bcnt, dyh, st)
