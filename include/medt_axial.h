@@ -153,7 +153,10 @@ int mt_conv1x1_backward(int N, int Ci, int Co, int H, int W, int stride, int rel
  * of a forward (bit 0 k_proj, 1 k_sim_stats, 2 k_attn, 3 k_out) or backward (bit 0
  * k_bwd_gather, 1 k_bwd_simstats, 2 k_bwd_attn, 3 k_bwd_proj) on buffers a full call has
  * already filled.  Statistic accumulators are NOT re-zeroed, so outputs are meaningless;
- * durations are those of the real launches.  Mask 15 == the full call minus the memsets. */
+ * durations are those of the real launches.  Mask 15 == the full launch CHAIN minus the memsets (the round-1 path, kept for
+ * shapes the cooperative kernels do not cover).  Mask 0x3f == the DEFAULT path: the persistent cooperative kernel of the op
+ * (k_axial_fwd / k_axial_bwd, one launch) with its accumulator memset and, for backward, WITHOUT the weight-gradient GEMM
+ * that a full call forks onto the side stream -- results are valid, this is what bench.py's roofline times. */
 int mt_axial_forward_stages(const MtAxialDesc* d, const MtAxialParams* p, const float* x, float* out,
                             void* saved, void* stream, int stage_mask);
 int mt_axial_backward_stages(const MtAxialDesc* d, const MtAxialParams* p, const float* x, const float* dout,

@@ -413,13 +413,15 @@ int axial_backward_launch(const Dims& m, const MtAxialParams& p, const float* x,
   int nl = 0;
   // default: ONE persistent cooperative kernel (axial_coop_bwd.cu) + the weight-gradient GEMM on the side stream.
   // MT_DEBUG_FLAGS bit5, the per-stage profiling entry point and shapes it does not cover use the launch chain below.
+  const bool coop_only = mask == 0x3f;       // profiling hook: the cooperative kernel alone (no dW GEMM on the side stream)
+  if (coop_only) mask = 0x1f;
   if (mask == 0x1f && !(m.dbg & 32)) {
     if (m.pos && !gr.drelative) return -3;
     if (cudaMemsetAsync(ws + m.ws_bstats, 0, m.ws_zero_bytes, st) != cudaSuccess) return -1;
     const int rc = launch_coop_bwd(m, p, gr, x, dout, stats, coef, yraw, oraw, lse, bstats, bcoef, bcnt, dyh, st);
     if (rc < 0) return -1;
     if (rc > 0) {
-      *nlaunch = rc + launch_bwd_dw(m, gr, x, bcoef, yraw, dyh, st);
+      *nlaunch = rc + (coop_only ? 0 : launch_bwd_dw(m, gr, x, bcoef, yraw, dyh, st));
       g_last_cuda = cudaGetLastError();
       return g_last_cuda == cudaSuccess ? 0 : -1;
     }

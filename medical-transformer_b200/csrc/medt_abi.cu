@@ -112,7 +112,7 @@ int mt_axial_forward(const MtAxialDesc* d, const MtAxialParams* p, const float* 
 }
 int mt_axial_forward_stages(const MtAxialDesc* d, const MtAxialParams* p, const float* x, float* out, void* saved,
                             void* stream, int stage_mask) {
-  return forward_impl(d, p, x, out, saved, stream, stage_mask & 0xf);
+  return forward_impl(d, p, x, out, saved, stream, stage_mask == 0x3f ? 0x1f : (stage_mask & 0xf));
 }
 
 static int backward_impl(const MtAxialDesc* d, const MtAxialParams* p, const float* x, const float* dout,
@@ -138,7 +138,7 @@ int mt_axial_backward(const MtAxialDesc* d, const MtAxialParams* p, const float*
 int mt_axial_backward_stages(const MtAxialDesc* d, const MtAxialParams* p, const float* x, const float* dout,
                              const void* saved, void* workspace, const MtAxialGrads* g, void* stream,
                              int stage_mask) {
-  return backward_impl(d, p, x, dout, saved, workspace, g, stream, stage_mask & 0xf);
+  return backward_impl(d, p, x, dout, saved, workspace, g, stream, stage_mask == 0x3f ? 0x3f : (stage_mask & 0xf));
 }
 
 }  // extern "C"

@@ -191,6 +191,7 @@ if __name__ == "__main__":
         make_model("axialunet_128", "axialunet", 128, 2)
         make_model("logo_128", "logo", 128, 2)
         make_model("MedT_256", "MedT", 256, 1, modes=("eval",), with_grads=False)
+        make_model("MedT_256_train", "MedT", 256, 2, modes=("train",))      # BASELINE config 3 in train mode (round 2)
 
 
 def make_schema():
