@@ -17,6 +17,7 @@
 // (dX sums over all heads), reading the other head groups' dy from the workspace.
 #include "axial_coop.cuh"
 #include "axial_diag_tile.cuh"
+#include "axial_fused_bwd.cuh"
 extern thread_local cudaError_t g_last_cuda;
 
 struct CoopPlanB {
@@ -29,6 +30,9 @@ struct CoopPlanB {
   int o_ca, o_cb, o_wsim, o_sA, o_sB, o_sC, o_oA, o_oB, o_oC, o_redo, o_reds, o_redq, o_rp, o_rs, o_drel, o_slot;
   int f_yn, f_do, f_gs, f_dl, f_ls, f_dy, slot_fl;          // offsets inside a slot
   int o_qA, o_qB, o_qC, o_w4, o_dyr, o_dxs;                 // B4 staging (aliases the slots)
+  // single-sweep path (axial_fused_bwd.cuh): lanes per (strip, head) group, segments of L/RT diagonal blocks, extra carve
+  int fused, NLg, NSEG, VP, o_wtab, o_gram, o_vacc;
+  DivS dNL;
   size_t smem_bytes;
 };
 
@@ -73,6 +77,8 @@ __device__ __forceinline__ void gemm_smem(const float* __restrict__ Wt, int WTP,
   }
 }
 
+__device__ __forceinline__ float warp_sum32(float v) { return seg_sum(v, 32); }
+
 // BN backward coefficients of one channel from the forward / backward fp64 accumulators (one out-of-line copy)
 __device__ __forceinline__ BnBwdCoef bwd_coef_from_stats(const Dims& m, const double* stats, const double* bstats, int grp,
                                                              int f_sum, int f_sq, int fch, double inv_n, float f, float gamma,
@@ -86,8 +92,11 @@ __device__ __forceinline__ BnBwdCoef bwd_coef_from_stats(const Dims& m, const do
 
 }  // namespace
 
-template <int D, bool POS, int RT>
-__global__ void __launch_bounds__(MT_COOP_THREADS, (D <= 2 ? 2 : 1))
+// symmetric pair index of (c, c') in a D x D matrix stored as its upper triangle
+__device__ __forceinline__ int sym_idx(int c, int e, int D_) { if (c > e) { const int t = c; c = e; e = t; } return c * D_ - (c * (c - 1)) / 2 + (e - c); }
+
+template <int D, bool POS, int RT, bool FUSED>
+__global__ void __launch_bounds__(MT_COOP_THREADS, ((D <= 2 && !FUSED) || (FUSED && D * RT <= 2) ? 2 : 1))
 k_axial_bwd(Dims m, MtAxialParams p, MtAxialGrads gr, CoopPlanB pl, const float* __restrict__ x, const float* __restrict__ dout,
             const double* __restrict__ stats, const float* __restrict__ coef, const float* __restrict__ yraw,
             const float* __restrict__ oraw, const float* __restrict__ lse, double* __restrict__ bstats,
@@ -122,6 +131,33 @@ k_axial_bwd(Dims m, MtAxialParams p, MtAxialGrads gr, CoopPlanB pl, const float*
   if (POS && cta == 0) for (int k = tid; k < nrel; k += blockDim.x) gr.drelative[k] = 0.f;     // accumulated after barrier 2
   if (cta == 0 && tid < 4 && gr.dgates) gr.dgates[tid] = 0.f;                                  // accumulated after barrier 3
   for (int k = tid; k < 24; k += blockDim.x) reds[k] = 0.f;
+  constexpr int DD = D * (D + 1) / 2;
+  float* wtab = sm + pl.o_wtab;    // FUSED: PRq [D][L] | PRk [D][L] | Mq [DD][L] | Mk [DD][L]  (window sums of the Toeplitz tables)
+  float* gram = sm + pl.o_gram;    // FUSED: per (strip, head) of the unit: K K^T [DD] | sum k [D] | Q Q^T [DD] | sum q [D]
+  float* vacc = sm + pl.o_vacc;    // FUSED: Vq [DD][VP] | Bq [D][VP] | Vk [DD][VP] | Bk [D][VP]: S-parts of d relative, summed over the CTA's units
+  if constexpr (FUSED) {
+    if (POS && train) {
+      __syncthreads();                                        // Rp staged
+      const int ntab = 2 * (D + DD);
+      for (int it = tid; it < ntab * L; it += blockDim.x) {
+        const int tb = dv(it, pl.dL), i = it - tb * L;
+        int c = 0, e = 0;
+        const float* base = Rp;
+        if (tb < 2 * D) { c = tb < D ? tb : tb - D; e = -1; base = Rp + (tb < D ? 0 : D) * RP; }
+        else {
+          int pi = tb - 2 * D;
+          if (pi >= DD) { pi -= DD; base = Rp + D * RP; }
+          for (c = 0; c < D; ++c) { if (pi < D - c) { e = c + pi; break; } pi -= D - c; }
+        }
+        const float* ra = base + c * RP + i;
+        float acc = 0.f;
+        if (e < 0) { for (int j = 0; j < L; ++j) acc += ra[j]; }
+        else { const float* rb = base + e * RP + i; for (int j = 0; j < L; ++j) acc = fmaf(ra[j], rb[j], acc); }
+        wtab[it] = acc;
+      }
+      for (int k = tid; k < 2 * (DD + D) * pl.VP; k += blockDim.x) vacc[k] = 0.f;
+    }
+  }
 
   // ================================================================== B1: g strips, o_raw, bn_output backward sums
   {
@@ -263,8 +299,77 @@ k_axial_bwd(Dims m, MtAxialParams p, MtAxialGrads gr, CoopPlanB pl, const float*
     __syncthreads();
   };
 
+  // ================================================================== B2 (single-sweep path): every L x L quantity in ONE pass
+  if constexpr (FUSED) {
+    const int NL = pl.NLg, NSEG = pl.NSEG;
+    int cur = -1;
+    for (int k = 0; k < pl.upc; ++k) {
+      const int u = pl.contig ? cta * pl.upc + k : cta + k * G;
+      if (u >= pl.nunits) break;
+      const int b0 = (u / HS) * SPU, grp = b0 / m.Bg;
+      float* slot = slots + (size_t)(pl.resident ? k : 0) * pl.slot_fl;
+      __syncthreads();
+      if (grp != cur) {
+        if (cur >= 0) {
+          double* bs = stat_slot(m, bstats, cur, m.nstat_b, cta);
+          if (tid < NT * HPU) { const int t = tid / HPU, g = hg * HPU + tid % HPU; MT_GADD(m, bs + m.b_sim_t + t * MT_G + g, (double)reds[t * MT_G + g]); }
+          __syncthreads();
+          if (tid < 24) reds[tid] = 0.f;
+        }
+        group_coefs(grp);
+        if (tid < NT * HPU) {           // A_t of the bn_similarity backward does not depend on T: known before the barrier
+          const int t = tid / HPU, g = hg * HPU + tid % HPU, ch = t * MT_G + g;
+          const float f = t == 0 ? 1.f : (t == 1 ? gate_val(p.f_qr) : gate_val(p.f_kr));
+          BnBwdCoef c = bwd_coef_from_stats(m, stats, bstats, grp, m.f_sim_sum, m.f_sim_sq, ch, m.inv_n2, f, p.bn_sim_w[ch],
+                                            p.bn_sim_rv[ch], 0, m.b_sim_t + ch, true);
+          sA[ch] = c.A;
+        }
+        cur = grp;
+        __syncthreads();
+      }
+      stage_unit(slot, b0, pl.resident != 0);
+      const float* Yn = slot + pl.f_yn; const float* dOs = slot + pl.f_do; const float* Dl = slot + pl.f_dl; const float* Ls = slot + pl.f_ls;
+      float* dY = slot + pl.f_dy;
+      for (int i = tid; i < SPU * RU * L; i += blockDim.x) dY[i] = 0.f;
+      __syncthreads();
+      const int nit = SPU * HPU * NL;
+      for (int base = 0; base < nit; base += blockDim.x) {
+        if (base + (tid & ~31) >= nit) break;                  // whole warp idle
+        const int item = base + tid;
+        const bool act = item < nit && !(m.dbg & 4);
+        const int it = item < nit ? item : 0;
+        const int gi = dv(it, pl.dNL), lig = tid & (NL - 1), s = dv(gi, pl.dHPU), hl = gi - s * HPU, g = hg * HPU + hl;
+        mtf::Coefs cf;
+        cf.wqk = wsim[g]; cf.wqr = POS ? wsim[MT_G + g] : 0.f; cf.wkr = POS ? wsim[2 * MT_G + g] : 0.f;
+        cf.A1 = sA[g]; cf.A2 = POS ? sA[MT_G + g] : 0.f; cf.A3 = POS ? sA[2 * MT_G + g] : 0.f;
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+        for (int sg = 0; sg < NSEG; ++sg)
+          mtf::fused_item<D, POS, RT>(L, RP, sg * NL + lig, lig, NL, NSEG == 1, act, Yn + ((size_t)s * RU + hl * 4 * D) * L,
+                                      dOs + ((size_t)s * NOCU + hl * GP * NO) * L, Ls + (s * HPU + hl) * L, Dl + (s * HPU + hl) * L,
+                                      Rp, cf, dRs, dY + ((size_t)s * RU + hl * 4 * D) * L, t0, t1, t2);
+        t0 = seg_sum(t0, NL);
+        if (POS) { t1 = seg_sum(t1, NL); t2 = seg_sum(t2, NL); }
+        if (act && lig == 0) {
+          atomicAdd(reds + g, t0);
+          if (POS) { atomicAdd(reds + MT_G + g, t1); atomicAdd(reds + 2 * MT_G + g, t2); }
+        }
+      }
+      if (!pl.resident) {                                      // streamed unit: the dZ parts wait in the workspace for the barrier
+        __syncthreads();
+        for (int i = tid; i < SPU * RU * L; i += blockDim.x) {
+          const int row = dv(i, pl.dL), l = i - row * L, s = dv(row, pl.dRU), r = row - s * RU;
+          dyh[((size_t)(b0 + s) * 2 * C + row0 + r) * L + l] = dY[i];
+        }
+      }
+    }
+    if (cur >= 0) {
+      __syncthreads();
+      double* bs = stat_slot(m, bstats, cur, m.nstat_b, cta);
+      if (tid < NT * HPU) { const int t = tid / HPU, g = hg * HPU + tid % HPU; MT_GADD(m, bs + m.b_sim_t + t * MT_G + g, (double)reds[t * MT_G + g]); }
+    }
+  }
   // ================================================================== B2: T[t,head] = sum dZ * S_t
-  {
+  if constexpr (!FUSED) {
     int cur = -1;
     for (int k = 0; k < pl.upc; ++k) {
       const int u = pl.contig ? cta * pl.upc + k : cta + k * G;
@@ -371,8 +476,208 @@ k_axial_bwd(Dims m, MtAxialParams p, MtAxialGrads gr, CoopPlanB pl, const float*
   grid_barrier(bar, G, epoch);
   phase_stamp(m, 4);
 
+  // ================================================================== B3 (single-sweep path): T is complete -> add the closed-form
+  // S_t / constant parts of dS_t = A_t dZ + Cc_t S_t + Bc_t  (no pair sweep), then the bn_qkv backward sums
+  if constexpr (FUSED) {
+    int cur = -1;
+    for (int k = 0; k < pl.upc; ++k) {
+      const int u = pl.contig ? cta * pl.upc + k : cta + k * G;
+      if (u >= pl.nunits) break;
+      const int b0 = (u / HS) * SPU, grp = b0 / m.Bg;
+      float* slot = slots + (size_t)(pl.resident ? k : 0) * pl.slot_fl;
+      __syncthreads();
+      if (grp != cur) {
+        if (cur >= 0) {
+          double* bs = stat_slot(m, bstats, cur, m.nstat_b, cta);
+          for (int r = tid; r < RU; r += blockDim.x) {
+            MT_GADD(m, bs + m.b_qkv_s1 + row0 + r, (double)redq[2 * r]);
+            MT_GADD(m, bs + m.b_qkv_s2 + row0 + r, (double)redq[2 * r + 1]);
+          }
+          __syncthreads();
+        }
+        if (!pl.resident) group_coefs(grp);
+        else {                                               // bn_qkv forward affine of THIS group (the stats below invert it)
+          const float* tq = coef + (size_t)grp * m.ncoef_f + m.cf_q;
+          for (int r = tid; r < RU; r += blockDim.x) { ca[r] = tq[2 * (row0 + r)]; cb[r] = tq[2 * (row0 + r) + 1]; }
+        }
+        if (tid < NT * HPU) {
+          const int t = tid / HPU, g = hg * HPU + tid % HPU, ch = t * MT_G + g;
+          const float f = t == 0 ? 1.f : (t == 1 ? gate_val(p.f_qr) : gate_val(p.f_kr));
+          BnBwdCoef c = bwd_coef_from_stats(m, stats, bstats, grp, m.f_sim_sum, m.f_sim_sq, ch, m.inv_n2, f, p.bn_sim_w[ch],
+                                            p.bn_sim_rv[ch], 0, m.b_sim_t + ch, true);
+          sA[ch] = c.A; sB[ch] = c.Bc; sC[ch] = c.Cc;
+        }
+        for (int r = tid; r < 2 * RU; r += blockDim.x) redq[r] = 0.f;
+        cur = grp;
+        __syncthreads();
+      }
+      float* Yn = slot + pl.f_yn;
+      float* dY = slot + pl.f_dy;
+      if (!pl.resident) {
+        stage_unit(slot, b0, false);
+        for (int i = tid; i < SPU * RU * L; i += blockDim.x) {
+          const int row = dv(i, pl.dL), l = i - row * L, s = dv(row, pl.dRU), r = row - s * RU;
+          dY[i] = __ldcg(dyh + ((size_t)(b0 + s) * 2 * C + row0 + r) * L + l);
+        }
+        __syncthreads();
+      }
+      if (train) {
+        // Gram matrices and sums of the unit's heads: one warp per (strip, head)
+        const int w = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+        for (int gi = w; gi < SPU * HPU; gi += nw) {
+          const int s = dv(gi, pl.dHPU), hl = gi - s * HPU;
+          const float* Yb = Yn + ((size_t)s * RU + hl * 4 * D) * L;
+          float kk[DD], qq[DD], ks[D], qs[D];
+#pragma unroll
+          for (int e = 0; e < DD; ++e) { kk[e] = 0.f; qq[e] = 0.f; }
+#pragma unroll
+          for (int c = 0; c < D; ++c) { ks[c] = 0.f; qs[c] = 0.f; }
+          for (int j = lane; j < L; j += 32) {
+            float qv[D], kv[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) { qv[c] = Yb[c * L + j]; kv[c] = Yb[(D + c) * L + j]; qs[c] += qv[c]; ks[c] += kv[c]; }
+            int e = 0;
+#pragma unroll
+            for (int c = 0; c < D; ++c)
+#pragma unroll
+              for (int f = c; f < D; ++f) { kk[e] = fmaf(kv[c], kv[f], kk[e]); qq[e] = fmaf(qv[c], qv[f], qq[e]); ++e; }
+          }
+          float* gm = gram + (size_t)gi * (2 * DD + 2 * D);
+#pragma unroll
+          for (int e = 0; e < DD; ++e) { kk[e] = warp_sum32(kk[e]); qq[e] = warp_sum32(qq[e]); }
+#pragma unroll
+          for (int c = 0; c < D; ++c) { ks[c] = warp_sum32(ks[c]); qs[c] = warp_sum32(qs[c]); }
+          if (lane == 0) {
+#pragma unroll
+            for (int e = 0; e < DD; ++e) { gm[e] = kk[e]; gm[DD + D + e] = qq[e]; }
+#pragma unroll
+            for (int c = 0; c < D; ++c) { gm[DD + c] = ks[c]; gm[2 * DD + D + c] = qs[c]; }
+          }
+        }
+        __syncthreads();
+        const float* PRq = wtab; const float* PRk = wtab + D * L; const float* Mq = wtab + 2 * D * L; const float* Mk = Mq + DD * L;
+        for (int it = tid; it < SPU * HPU * L; it += blockDim.x) {
+          const int gi = dv(it, pl.dL), i = it - gi * L, s = dv(gi, pl.dHPU), hl = gi - s * HPU, g = hg * HPU + hl;
+          const float* Yb = Yn + ((size_t)s * RU + hl * 4 * D) * L;
+          float* dYb = dY + ((size_t)s * RU + hl * 4 * D) * L;
+          const float* gm = gram + (size_t)gi * (2 * DD + 2 * D);
+          const float C1 = sC[g], B1 = sB[g];
+          const float C2 = POS ? sC[MT_G + g] : 0.f, B2 = POS ? sB[MT_G + g] : 0.f, C3 = POS ? sC[2 * MT_G + g] : 0.f, B3 = POS ? sB[2 * MT_G + g] : 0.f;
+          float qv[D], kv[D];
+#pragma unroll
+          for (int c = 0; c < D; ++c) { qv[c] = Yb[c * L + i]; kv[c] = Yb[(D + c) * L + i]; }
+#pragma unroll
+          for (int c = 0; c < D; ++c) {
+            float kkq = 0.f, qqk = 0.f, mq = 0.f, mk = 0.f;
+#pragma unroll
+            for (int e = 0; e < D; ++e) {
+              const int si = sym_idx(c, e, D);
+              kkq = fmaf(gm[si], qv[e], kkq); qqk = fmaf(gm[DD + D + si], kv[e], qqk);
+              if (POS) { mq = fmaf(Mq[si * L + i], qv[e], mq); mk = fmaf(Mk[si * L + i], kv[e], mk); }
+            }
+            float aq = fmaf(C1, kkq, B1 * gm[DD + c]), ak = fmaf(C1, qqk, B1 * gm[2 * DD + D + c]);
+            if (POS) { aq += fmaf(C2, mq, B2 * PRq[c * L + i]); ak += fmaf(C3, mk, B3 * PRk[c * L + i]); }
+            dYb[c * L + i] += aq; dYb[(D + c) * L + i] += ak;
+          }
+        }
+        if (POS) {
+          // S-parts of d relative: per position i, summed over the unit's (strip, head)s with their coefficients
+          const int VP = pl.VP;
+          for (int i = tid; i < L; i += blockDim.x) {
+            float vq[DD], vk[DD], bq[D], bk[D];
+#pragma unroll
+            for (int e = 0; e < DD; ++e) { vq[e] = 0.f; vk[e] = 0.f; }
+#pragma unroll
+            for (int c = 0; c < D; ++c) { bq[c] = 0.f; bk[c] = 0.f; }
+            for (int gi = 0; gi < SPU * HPU; ++gi) {
+              const int s = dv(gi, pl.dHPU), hl = gi - s * HPU, g = hg * HPU + hl;
+              const float* Yb = Yn + ((size_t)s * RU + hl * 4 * D) * L;
+              const float C2 = sC[MT_G + g], B2 = sB[MT_G + g], C3 = sC[2 * MT_G + g], B3 = sB[2 * MT_G + g];
+              float qv[D], kv[D];
+#pragma unroll
+              for (int c = 0; c < D; ++c) { qv[c] = Yb[c * L + i]; kv[c] = Yb[(D + c) * L + i]; bq[c] = fmaf(B2, qv[c], bq[c]); bk[c] = fmaf(B3, kv[c], bk[c]); }
+              int e = 0;
+#pragma unroll
+              for (int c = 0; c < D; ++c)
+#pragma unroll
+                for (int f = c; f < D; ++f) { vq[e] = fmaf(C2 * qv[c], qv[f], vq[e]); vk[e] = fmaf(C3 * kv[c], kv[f], vk[e]); ++e; }
+            }
+#pragma unroll
+            for (int e = 0; e < DD; ++e) { vacc[e * VP + i] += vq[e]; vacc[(DD + D + e) * VP + i] += vk[e]; }
+#pragma unroll
+            for (int c = 0; c < D; ++c) { vacc[(DD + c) * VP + i] += bq[c]; vacc[(2 * DD + D + c) * VP + i] += bk[c]; }
+          }
+        }
+        __syncthreads();
+      }
+      // dy (w.r.t. the normalised projection) -> workspace for B4 / k_bwd_dw
+      for (int i = tid; i < SPU * RU * L; i += blockDim.x) {
+        const int row = dv(i, pl.dL), l = i - row * L, s = dv(row, pl.dRU), r = row - s * RU;
+        dyh[((size_t)(b0 + s) * 2 * C + row0 + r) * L + l] = dY[i];
+      }
+      // bn_qkv backward sums: s1 = sum dy, s2 = sum dy * y_raw.  The staged rows hold yn = ca*y_raw + cb, so
+      // s2 = (sum dy*yn - cb*s1) / ca straight from shared memory (no L2 round trip); a zero scale falls back to y_raw
+      {
+        const int tpr = pl.tpr_q, sub = tid & (tpr - 1), rpp = blockDim.x / tpr;
+        for (int r0 = 0; r0 < RU; r0 += rpp) {
+          const int r = r0 + tid / tpr;
+          float a1 = 0.f, a2 = 0.f;
+          const float car = r < RU ? ca[r] : 1.f;
+          if (r < RU)
+            for (int s = 0; s < SPU; ++s) {
+              const float* dy = dY + ((size_t)s * RU + r) * L;
+              if (car != 0.f) {
+                const float* yn = Yn + ((size_t)s * RU + r) * L;
+                for (int l = sub; l < L; l += tpr) { const float d = dy[l]; a1 += d; a2 = fmaf(d, yn[l], a2); }
+              } else {
+                const float* yr = yraw + ((size_t)(b0 + s) * 2 * C + row0 + r) * L;
+                for (int l = sub; l < L; l += tpr) { const float d = dy[l]; a1 += d; a2 = fmaf(d, __ldg(yr + l), a2); }
+              }
+            }
+          a1 = seg_sum(a1, tpr); a2 = seg_sum(a2, tpr);
+          if (sub == 0 && r < RU) {
+            redq[2 * r] += a1;
+            redq[2 * r + 1] += car != 0.f ? (a2 - cb[r] * a1) / car : a2;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (cur >= 0) {
+      double* bs = stat_slot(m, bstats, cur, m.nstat_b, cta);
+      for (int r = tid; r < RU; r += blockDim.x) {
+        MT_GADD(m, bs + m.b_qkv_s1 + row0 + r, (double)redq[2 * r]);
+        MT_GADD(m, bs + m.b_qkv_s2 + row0 + r, (double)redq[2 * r + 1]);
+      }
+    }
+    if (POS && train) {
+      // d relative[c, m] += sum_e R[e, m] * RS(V[c,e]) + RS(B[c]),  RS = sum over the rows (columns) i of diagonal m: direct sums
+      // (O(L) each, once per CTA; no prefix differences -> no cancellation)
+      const int VP = pl.VP;
+      for (int it = tid; it < 2 * D * RL; it += blockDim.x) {
+        const int row = dv(it, pl.dRL), mm = it - row * RL;        // row in [0, 2D): q-table rows, then k-table rows
+        const bool isk = row >= D;
+        const int c = isk ? row - D : row;
+        const int dl = mm - (L - 1), lo = dl > 0 ? dl : 0, hi = dl < 0 ? L - 1 + dl : L - 1;
+        const float* V = vacc + (size_t)(isk ? DD + D : 0) * VP;
+        const float* Bv = V + (size_t)DD * VP + c * VP;
+        float acc = 0.f;
+        for (int i = lo; i <= hi; ++i) acc += Bv[i];
+#pragma unroll
+        for (int e = 0; e < D; ++e) {
+          const float* Vr = V + (size_t)sym_idx(c, e, D) * VP;
+          float rs = 0.f;
+          for (int i = lo; i <= hi; ++i) rs += Vr[i];
+          acc = fmaf(Rp[(size_t)(isk ? D + e : e) * RP + mm], rs, acc);
+        }
+        dRs[row * RL + mm] += acc;
+      }
+      __syncthreads();
+    }
+    if (POS) for (int k = tid; k < nrel; k += blockDim.x) MT_GADD(m, gr.drelative + k, dRs[k]);
+  }
   // ================================================================== B3: dq / dk, dv / d relative, bn_qkv backward sums
-  {
+  if constexpr (!FUSED) {
     int cur = -1;
     for (int k = 0; k < pl.upc; ++k) {
       const int u = pl.contig ? cta * pl.upc + k : cta + k * G;
@@ -794,7 +1099,32 @@ int coop_force_stream();
 int coop_env_int(const char* name);
 int coop_rows_tpr(int nrows, int L);
 
-static bool coop_plan_bwd_hs(const Dims& m, int maxctas, size_t smem_cap, CoopPlanB& pl, int hs_min) {
+// single-sweep path: RT of the wrapped-diagonal tile.  The NL = min(L/RT, 32) lanes of a (strip, head) must be a power of two and
+// at least D*RT (transposing row reduction); the largest RT that still fills the CTA's 256 threads wins.
+static int coop_rt_fused(const Dims& m, int groups_per_cta) {
+  static const int off = coop_env_int("MT_BWD_NOFUSE"), force = coop_env_int("MT_BWD_FUSED_RT"), all = coop_env_int("MT_BWD_FUSED_ALL");
+  if (off > 0 || m.d > 4 || (m.L & (m.L - 1)) != 0) return 0;
+  // measured (profiles/r2_notes.md): the single sweep wins where the L^2 work dominates -- d = 1 from L = 64, d = 2 at L = 64;
+  // short strips (the combine phase costs more than the sweeps it removes), d = 4 (1 x 1 tiles) and d = 2 at L >= 128 (250
+  // registers, one CTA per SM, four lanes groups per CTA) stay on the multi-sweep path.  MT_BWD_FUSED_ALL=1 lifts the policy.
+  if (!all && !force && !((m.d == 1 && m.L >= 64) || (m.d == 2 && m.L == 64))) return 0;
+  const int cand[3] = {4, 2, 1};
+  int best = 0;
+  bool filled = false;
+  for (int k = 0; k < 3; ++k) {
+    const int rt = cand[k];
+    if (rt * m.d > 4 || m.L % rt) continue;
+    const int lb = m.L / rt, nl = lb < 32 ? lb : 32;
+    if (nl < m.d * rt || nl < 2) continue;
+    if (force == rt) return rt;
+    if (filled) continue;
+    best = rt;                                       // smaller RT = more lanes
+    if (groups_per_cta * nl >= MT_COOP_THREADS) filled = true;
+  }
+  return best;
+}
+
+static bool coop_plan_bwd_hs(const Dims& m, int maxctas, size_t smem_cap, CoopPlanB& pl, int hs_min, int want_fused) {
   const int C = m.C, L = m.L, D = m.d, GP = 2 * D, NO = m.no;
   pl.RT = coop_rt_bwd(m);
   pl.LB = L / pl.RT;
@@ -846,6 +1176,17 @@ static bool coop_plan_bwd_hs(const Dims& m, int maxctas, size_t smem_cap, CoopPl
   pl.o_rp = take(m.pos ? 2 * m.gp * rel_pitch(L) : 0);
   pl.o_rs = take(m.pos ? 2 * m.gp * rel_pitch(L) : 0);
   pl.o_drel = take(m.pos ? 2 * m.gp * (2 * L - 1) : 0);
+  pl.fused = 0; pl.NLg = 1; pl.NSEG = 1; pl.VP = L + 1; pl.o_wtab = pl.o_gram = pl.o_vacc = off; pl.dNL = make_divs(1);
+  if (want_fused) {
+    const int rt = coop_rt_fused(m, pl.SPU * pl.HPU);
+    if (!rt) return false;
+    const int DD = D * (D + 1) / 2;
+    pl.fused = 1; pl.RT = rt; pl.LB = L / rt;
+    pl.NLg = pl.LB < 32 ? pl.LB : 32; pl.NSEG = pl.LB / pl.NLg; pl.dNL = make_divs(pl.NLg); pl.dLB = make_divs(pl.LB);
+    pl.o_wtab = take((m.pos && m.training) ? 2 * (D + DD) * L : 0);
+    pl.o_gram = take(pl.SPU * pl.HPU * (2 * DD + 2 * D));
+    pl.o_vacc = take((m.pos && m.training) ? 2 * (DD + D) * pl.VP : 0);
+  }
   pl.o_slot = off;
   int so = 0;
   auto stake = [&](int n) { int o = so; so += (n + 3) & ~3; return o; };
@@ -869,17 +1210,17 @@ static bool coop_plan_bwd_hs(const Dims& m, int maxctas, size_t smem_cap, CoopPl
   return true;
 }
 
-static bool coop_plan_bwd(const Dims& m, int maxctas, size_t smem_cap, CoopPlanB& pl) {
+static bool coop_plan_bwd(const Dims& m, int maxctas, size_t smem_cap, CoopPlanB& pl, int want_fused) {
   for (int hs = 1; hs <= MT_G; hs *= 2)
-    if (coop_plan_bwd_hs(m, maxctas, smem_cap, pl, hs)) return true;
+    if (coop_plan_bwd_hs(m, maxctas, smem_cap, pl, hs, want_fused)) return true;
   return false;
 }
 
-template <int D, bool POS, int RT>
+template <int D, bool POS, int RT, bool FUSED>
 static int coop_launch_bwd(const Dims& m, const MtAxialParams& p, const MtAxialGrads& gr, const float* x, const float* dout,
                            const double* stats, const float* coef, const float* yraw, const float* oraw, const float* lse,
                            double* bstats, float* bcoef, unsigned* bcnt, float* dyh, cudaStream_t st) {
-  auto kern = k_axial_bwd<D, POS, RT>;
+  auto kern = k_axial_bwd<D, POS, RT, FUSED>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess) return -1;
@@ -893,7 +1234,8 @@ static int coop_launch_bwd(const Dims& m, const MtAxialParams& p, const MtAxialG
     int maxctas = nsm * occ;
     if (cap > 0 && maxctas > cap) maxctas = cap;
     const size_t smem_cap = occ == 2 ? 110 * 1024 : 224 * 1024;
-    if (!coop_plan_bwd(m, maxctas, smem_cap, pl)) continue;
+    if (!coop_plan_bwd(m, maxctas, smem_cap, pl, FUSED ? 1 : 0)) continue;
+    if (FUSED && pl.RT != RT) continue;
     if (occ == 2) {
       if (pl.G <= nsm) { ok = true; break; }
       static thread_local size_t q_smem[8] = {0};
@@ -918,10 +1260,19 @@ static int coop_launch_bwd(const Dims& m, const MtAxialParams& p, const MtAxialG
 int launch_coop_bwd(const Dims& m, const MtAxialParams& p, const MtAxialGrads& gr, const float* x, const float* dout,
                     const double* stats, const float* coef, const float* yraw, const float* oraw, const float* lse,
                     double* bstats, float* bcoef, unsigned* bcnt, float* dyh, cudaStream_t st) {
+#define GOF(DD, RR)                                                                                                          \
+  { const int rc_ = m.pos ? coop_launch_bwd<DD, true, RR, true>(m, p, gr, x, dout, stats, coef, yraw, oraw, lse, bstats, bcoef, bcnt, dyh, st)   \
+                          : coop_launch_bwd<DD, false, RR, true>(m, p, gr, x, dout, stats, coef, yraw, oraw, lse, bstats, bcoef, bcnt, dyh, st); \
+    if (rc_ != 0) return rc_; }
+  // single-sweep path first (every RT the planner may pick for this d); the multi-sweep kernel below covers the rest
+  if (m.d == 1) { GOF(1, 4); GOF(1, 2); GOF(1, 1); }
+  if (m.d == 2) { GOF(2, 2); GOF(2, 1); }
+  if (m.d == 4) { GOF(4, 1); }
+#undef GOF
   const int rt = coop_rt_bwd(m);
 #define GO(DD, RR)                                                                                                          \
-  return m.pos ? coop_launch_bwd<DD, true, RR>(m, p, gr, x, dout, stats, coef, yraw, oraw, lse, bstats, bcoef, bcnt, dyh, st)   \
-               : coop_launch_bwd<DD, false, RR>(m, p, gr, x, dout, stats, coef, yraw, oraw, lse, bstats, bcoef, bcnt, dyh, st)
+  return m.pos ? coop_launch_bwd<DD, true, RR, false>(m, p, gr, x, dout, stats, coef, yraw, oraw, lse, bstats, bcoef, bcnt, dyh, st)   \
+               : coop_launch_bwd<DD, false, RR, false>(m, p, gr, x, dout, stats, coef, yraw, oraw, lse, bstats, bcoef, bcnt, dyh, st)
   if (m.d == 1) { if (rt == 4) { GO(1, 4); } if (rt == 2) { GO(1, 2); } GO(1, 1); }
   if (m.d == 2) { if (rt == 2) { GO(2, 2); } GO(2, 1); }
   if (m.d == 4) { if (rt == 2) { GO(4, 2); } GO(4, 1); }

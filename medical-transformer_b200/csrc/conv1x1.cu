@@ -58,8 +58,10 @@ k_c1_fwd(C1Args a, const float* __restrict__ x, const float* __restrict__ w, flo
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < a.Ci; k0 += 16) {
-    float va[4], vb[4];
+  // the K loop is a chain of L2-latency-bound chunk loads (a few CTAs per launch, nothing else to hide them): the loads of
+  // chunk k+1 are issued into registers before the FMAs of chunk k
+  float va[4], vb[4];
+  auto load_chunk = [&](int k0) {
 #pragma unroll
     for (int it = 0; it < 4; ++it) {                // A: W[co0+mm][k0+kk], thread -> kk = tid&15, mm = tid>>4 + 16 it
       const int kk = tid & 15, mm = (tid >> 4) + 16 * it;
@@ -68,12 +70,16 @@ k_c1_fwd(C1Args a, const float* __restrict__ x, const float* __restrict__ w, flo
       vb[it] = (pok && k0 + kb < a.Ci) ? __ldg(xb + (size_t)(k0 + kb) * HW) : 0.f;
       if (a.relu_in) vb[it] = fmaxf(vb[it], 0.f);
     }
+  };
+  load_chunk(0);
+  for (int k0 = 0; k0 < a.Ci; k0 += 16) {
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       As[(tid & 15) * C1_LD + (tid >> 4) + 16 * it] = va[it];
       Bs[((tid >> 6) + 4 * it) * C1_LD + (tid & 63)] = vb[it];
     }
     __syncthreads();
+    if (k0 + 16 < a.Ci) load_chunk(k0 + 16);
     c1_mma(As, Bs, ty, tx, acc);
     __syncthreads();
   }
@@ -106,20 +112,24 @@ k_c1_dx(C1Args a, const float* __restrict__ dy, const float* __restrict__ w, con
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < a.Co; k0 += 16) {
-    float va[4], vb[4];
+  float va[4], vb[4];
+  auto load_chunk = [&](int k0) {
 #pragma unroll
     for (int it = 0; it < 4; ++it) {                // A: W^T: As[kk][mm] = W[k0+kk][ci0+mm]; thread -> mm = tid&63, kk = tid>>6 + 4 it
       const int mm = tid & 63, kk = (tid >> 6) + 4 * it;
       va[it] = (ci0 + mm < a.Ci && k0 + kk < a.Co) ? __ldg(w + (size_t)(k0 + kk) * a.Ci + ci0 + mm) : 0.f;
       vb[it] = (pok && k0 + kk < a.Co) ? __ldg(yb + (size_t)(k0 + kk) * HWo) : 0.f;
     }
+  };
+  load_chunk(0);
+  for (int k0 = 0; k0 < a.Co; k0 += 16) {
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       As[((tid >> 6) + 4 * it) * C1_LD + (tid & 63)] = va[it];
       Bs[((tid >> 6) + 4 * it) * C1_LD + (tid & 63)] = vb[it];
     }
     __syncthreads();
+    if (k0 + 16 < a.Co) load_chunk(k0 + 16);        // next chunk in flight during this chunk's FMAs
     c1_mma(As, Bs, ty, tx, acc);
     __syncthreads();
   }

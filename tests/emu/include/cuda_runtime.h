@@ -98,6 +98,7 @@ template <class T> static inline T emu_exchange(T v, int src_lane_in_warp) {
 }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) { return emu_exchange(v, (emu::lin() & 31) ^ lane_mask); }
 template <class T> static inline T __shfl_sync(unsigned, T v, int src_lane) { return emu_exchange(v, src_lane); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { (void)emu_exchange(0, (int)(emu::lin() & 31)); }     // warp collective == scheduler barrier
 static inline int __all_sync(unsigned, int pred) { return emu::all(pred); }
 // atomics go through the compiler builtins so that ThreadSanitizer (tests/emu/run_tsan.sh) sees them as atomics
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }

@@ -1,7 +1,13 @@
-"""GPU tier, OPT-IN (MEDT_EXPERIMENTAL=1): the unmeasured k_bwd2 variants behind MT_DEBUG_FLAGS bits 3 / 4
-(8 = register-tiled wrapped-diagonal d-relative pass, 16 = rows / columns in separate CTAs, 24 = both) must pass the
-same op-level parity suite as the default kernels.  The flags are read once per process, hence the subprocesses.
-Not part of the default run: these variants have not been on a GPU yet."""
+"""GPU tier: every alternate code path of the axial op that ships in libmedt_b200.so must pass the same op-level parity suite
+(tests/test_gpu_axial.py: reference goldens + oracle at the baseline sizes) as the default path.  The selectors are read once
+per process, hence the subprocesses.
+
+  default                 single-sweep cooperative backward where the planner picks it, multi-sweep cooperative elsewhere
+  MT_BWD_NOFUSE=1         multi-sweep cooperative backward everywhere (the round-2a kernel; serves d = 4 / 8 and short strips)
+  MT_BWD_FUSED_ALL=1      single-sweep backward wherever it is applicable (d <= 4, power-of-two lengths), incl. 1 x 1 tiles
+  MT_COOP_STREAM=1        cooperative kernels in streamed (non-resident) mode, as at 512 px
+  MT_DEBUG_FLAGS=32       round-1 launch chain (what shapes the cooperative planners reject fall back to)
+  MT_DEBUG_FLAGS=40/48/56 launch chain with the tiled wrapped-diagonal d-relative pass / split row-column CTAs / both"""
 import os
 import subprocess
 import sys
@@ -12,10 +18,10 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.skipif(os.environ.get("MEDT_EXPERIMENTAL") != "1", reason="opt-in: MEDT_EXPERIMENTAL=1")
-@pytest.mark.parametrize("flags", [8, 16, 24])
-def test_experimental_bwd_variants_pass_the_axial_parity_suite(flags):
-    env = dict(os.environ, MT_DEBUG_FLAGS=str(flags))
+@pytest.mark.parametrize("env", [{"MT_BWD_NOFUSE": "1"}, {"MT_BWD_FUSED_ALL": "1"}, {"MT_COOP_STREAM": "1", "MT_BWD_FUSED_ALL": "1"},
+                                 {"MT_DEBUG_FLAGS": "32"}, {"MT_DEBUG_FLAGS": "40"}, {"MT_DEBUG_FLAGS": "48"}, {"MT_DEBUG_FLAGS": "56"}],
+                         ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
+def test_alternate_paths_pass_the_axial_parity_suite(env):
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "tests", "test_gpu_axial.py"), "-q", "-x", "-m", "gpu"],
-                       env=env, capture_output=True, text=True, timeout=900, cwd=HERE)
+                       env=dict(os.environ, **env), capture_output=True, text=True, timeout=900, cwd=HERE)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]

@@ -220,7 +220,6 @@ def test_predictor_masks_equal_thresholded_eval_logits(tmp_path):
     assert np.array_equal(cv2.imread(str(tmp_path / "002.png"), cv2.IMREAD_GRAYSCALE), got[1])
 
 
-@pytest.mark.skipif(os.environ.get("MEDT_EXPERIMENTAL") != "1", reason="opt-in: MEDT_EXPERIMENTAL=1 (graph-captured inference not yet run on a GPU)")
 def test_predictor_graph_equals_eager():
     from medt_b200.infer import Predictor
     m = build_filled_model("gated", 64, device="cuda").eval()

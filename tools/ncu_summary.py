@@ -33,13 +33,13 @@ def summarise(path):
                 out.append(f"| {k} | {d[hit[0]]} | {u[hit[0]]} |")
         stalls = []
         for h in head:
-            if "warp_issue_stalled" in h and h.endswith("per_warp_active.pct"):
+            if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio"):
                 try:
-                    stalls.append((float(d[h].replace(",", "")), h.split("warp_issue_stalled_")[1].replace("_per_warp_active.pct", "")))
+                    stalls.append((float(d[h].replace(",", "")), h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]))
                 except ValueError:
                     pass
         stalls.sort(reverse=True)
-        out.append("| top stalls (% of warp-active cycles) | " + ", ".join(f"{n} {v:.1f}" for v, n in stalls[:7]) + " | |")
+        out.append("| stalled warps per issue-active cycle, by reason | " + ", ".join(f"{n} {v:.2f}" for v, n in stalls[:8]) + " | |")
         out.append("")
     return "\n".join(out)
 
