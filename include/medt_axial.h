@@ -12,6 +12,7 @@
  *   mt_bn_act_*        <- BatchNorm2d(+ReLU)(+residual) glue of the blocks / stems / LoGo loop
  *   mt_up2x_relu_add_* <- relu(bilinear x2) + skip of the decoders
  *   mt_conv1x1_*       <- the bias-free 1x1 convolutions of the blocks
+ *   mt_conv2d_*        <- the KxK convolutions of the stems and decoders
  *
  * Conventions
  *   - plain C, no torch types; all pointers are DEVICE pointers unless named host_*;
@@ -148,6 +149,17 @@ int mt_conv1x1_forward(int N, int Ci, int Co, int H, int W, int stride, int relu
                        float* y, void* stream);
 int mt_conv1x1_backward(int N, int Ci, int Co, int H, int W, int stride, int relu_in, const float* x, const float* w,
                         const float* dy, float* dx, float* dw, void* stream);
+
+/* KxK convolution of the conv shell (stem conv2 / conv3 `axialnet.py:424-428,478-483`, the decoder convs `:431-440,493-502`,
+ * LoGo's `decoderf` `:585`) as an implicit-GEMM fp32 kernel with split-K over the whole GPU (cuDNN's fp32 algorithms for these
+ * small-M x long-K problems run at 0.4 - 8 TFLOP/s).  x: (N,Ci,H,W), w: (Co,Ci,KH,KW), y / dy: (N,Co,Ho,Wo) with
+ * Ho = (H + 2 pad - KH) / stride + 1; no bias (the decoders' bias is added by mt_up2x_relu_add_forward), no dilation / groups.
+ * backward overwrites dx (N,Ci,H,W; stride 1 only: pass NULL otherwise -> MT_ERR_UNSUPPORTED) and dw (Co,Ci,KH,KW); either may be
+ * NULL.  Split-K slices accumulate with fp32 atomics: last-bit run-to-run differences. */
+int mt_conv2d_forward(int N, int Ci, int Co, int H, int W, int KH, int KW, int stride, int pad, const float* x, const float* w,
+                      float* y, void* stream);
+int mt_conv2d_backward(int N, int Ci, int Co, int H, int W, int KH, int KW, int stride, int pad, const float* x, const float* w,
+                       const float* dy, float* dx, float* dw, void* stream);
 
 /* Profiling hooks (bench.py roofline, ncu): launch only the stages selected by `stage_mask`
  * of a forward (bit 0 k_proj, 1 k_sim_stats, 2 k_attn, 3 k_out) or backward (bit 0

@@ -21,7 +21,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from medt_b200.axial_op import axial_attention
-from medt_b200.shell_ops import bn_act, conv1x1 as conv1x1_op, up2x_relu_add
+from medt_b200.shell_ops import bn_act, conv1x1 as conv1x1_op, conv2d, up2x_relu_add
 
 from .utils import qkv_transform
 
@@ -174,9 +174,9 @@ class AxialBlock_wopos(_AxialBlockBase):
 def _up_relu(conv, x, skip=None):
     """relu(bilinear x2 (conv(x))) [+ skip] -- one decoder step (reference :493-501), one fused kernel."""
     if conv.bias is None or os.environ.get("MEDT_NO_SHELL_FUSION"):
-        return up2x_relu_add(conv(x), skip)
+        return up2x_relu_add(conv2d(x, conv), skip)
     # the conv runs without its bias; the fused kernel adds it (the bilinear taps sum to 1) and reduces its gradient
-    y = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+    y = conv2d(x, conv, with_bias=False)
     return up2x_relu_add(y, skip, conv.bias)
 
 
@@ -211,7 +211,7 @@ class _ShellBase(nn.Module):
     @staticmethod
     def _stem(x, convs, bns, groups=1):
         for conv, bn in zip(convs, bns):
-            x = bn_act(conv(x), bn, groups, relu=True)
+            x = bn_act(conv2d(x, conv), bn, groups, relu=True)
         return x
 
 
@@ -360,7 +360,7 @@ class medt_net(_ShellBase):
         side_len = self._patch * GRID
         x_loc = x.clone()                       # outside the 128x128 patch grid x_loc stays == x (:658,:700)
         x_loc[:, :, :side_len, :side_len] = loc
-        x = F.relu(self.decoderf(x + x_loc))
+        x = F.relu(conv2d(x + x_loc, self.decoderf))
         return self.adjust(F.relu(x))
 
     def _side_stream(self, device):

@@ -7,6 +7,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -188,3 +190,72 @@ def conv1x1(x, conv, relu_in=False):
     if conv.bias is not None or conv.kernel_size != (1, 1):
         return conv(F.relu(x) if relu_in else x)
     return Conv1x1.apply(x, conv.weight, int(conv.stride[0]), bool(relu_in))
+
+
+class Conv2dGemm(torch.autograd.Function):
+    """KxK convolution on the implicit-GEMM split-K kernels of csrc/conv_gemm.cu.  `own_bwd`: dX (stride 1 only) and dW on the
+    same kernels; otherwise the backward is cuDNN's (torch.ops.aten.convolution_backward)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride, pad, own_bwd):
+        _need_cuda(x, "conv2d")
+        lib = _cabi.load_library()
+        x = _cabi.dense(x)
+        weight = weight.contiguous()
+        n, ci, h, w = x.shape
+        co, _, kh, kw = weight.shape
+        ho, wo = (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1
+        y = torch.empty((n, co, ho, wo), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.mt_conv2d_forward(n, ci, co, h, w, kh, kw, stride, pad, _p(x), _p(weight), _p(y), _stream(x.device))
+        _cabi.check(rc, "mt_conv2d_forward")
+        _cabi.LAUNCHES["kernels"] += 1
+        ctx.save_for_backward(x, weight)
+        ctx.stride, ctx.pad, ctx.own_bwd = stride, pad, bool(own_bwd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = _cabi.dense(dy)
+        n, ci, h, w = x.shape
+        co, _, kh, kw = weight.shape
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not ctx.own_bwd:
+            dx, dw, _ = torch.ops.aten.convolution_backward(dy, x, weight, None, [ctx.stride] * 2, [ctx.pad] * 2, [1, 1], False, [0, 0], 1,
+                                                            [bool(need_dx), bool(need_dw), False])
+            return dx, dw, None, None, None
+        lib = _cabi.load_library()
+        own_dx = need_dx and ctx.stride == 1
+        dx = torch.empty_like(x) if own_dx else None
+        dw = torch.empty_like(weight) if need_dw else None
+        if own_dx or need_dw:
+            with torch.cuda.device(x.device):
+                rc = lib.mt_conv2d_backward(n, ci, co, h, w, kh, kw, ctx.stride, ctx.pad, _p(x), _p(weight), _p(dy), _p(dx), _p(dw),
+                                            _stream(x.device))
+            _cabi.check(rc, "mt_conv2d_backward")
+            _cabi.LAUNCHES["kernels"] += (1 if own_dx else 0) + (1 if need_dw else 0)
+        if need_dx and not own_dx:
+            dx = torch.ops.aten.convolution_backward(dy, x, weight, None, [ctx.stride] * 2, [ctx.pad] * 2, [1, 1], False, [0, 0], 1,
+                                                     [True, False, False])[0]
+        return dx, dw, None, None, None
+
+
+def conv2d(x, conv, with_bias=True):
+    """`conv` is the module's own nn.Conv2d (weight used in place).  Measured on B200 (tools/time_convs.py, profiles/r2_notes.md):
+    cuDNN's fp32 algorithms win on the stride-1 3x3 shapes of this network (15 - 27 TFLOP/s against 5 - 20 for the generic
+    implicit-GEMM kernel) but collapse on decoder1 (256 -> 256, stride 2, 8x8 -> 4x4: 16 CTAs, 105 - 172 us): that forward runs
+    on csrc/conv_gemm.cu (27 us, split-K over all SMs), everything else stays cuDNN (north_star: "the conv stem/decoder and
+    adjust blocks are cuDNN").  MEDT_OWN_CONV=all routes every eligible convolution (forward and backward) through the own
+    kernels, MEDT_OWN_CONV=none none."""
+    k = conv.kernel_size
+    mode = os.environ.get("MEDT_OWN_CONV", "strided")
+    ok = (k[0] == k[1] and conv.stride[0] == conv.stride[1] and isinstance(conv.padding, tuple) and conv.padding[0] == conv.padding[1]
+          and conv.dilation == (1, 1) and conv.groups == 1 and conv.padding_mode == "zeros" and x.is_cuda and x.dtype == torch.float32
+          and mode != "none" and (mode == "all" or (conv.stride[0] > 1 and k[0] == 3)))
+    if not ok:
+        return F.conv2d(x, conv.weight, conv.bias if with_bias else None, conv.stride, conv.padding, conv.dilation, conv.groups)
+    y = Conv2dGemm.apply(x, conv.weight, int(conv.stride[0]), int(conv.padding[0]), mode == "all")
+    if with_bias and conv.bias is not None:
+        y = y + conv.bias.view(1, -1, 1, 1)
+    return y

@@ -121,3 +121,34 @@ def test_misaligned_contiguous_views_give_the_same_result():
         a, b = fn(xa), fn(xv)
         # same kernels, same data: only the order of the fp64 statistic atomics differs between two launches
         assert (a - b).abs().max().item() <= 1e-5 * a.abs().max().item()
+
+
+@pytest.mark.parametrize("n,ci,co,h,k,stride,pad,bias", [(4, 8, 128, 64, 3, 1, 1, False),     # stem conv2
+                                                         (4, 128, 8, 64, 3, 1, 1, False),     # stem conv3 (8 output channels)
+                                                         (4, 256, 256, 8, 3, 2, 1, True),     # decoder1 (stride 2: dX via cuDNN)
+                                                         (4, 256, 128, 8, 3, 1, 1, True),     # decoder2
+                                                         (4, 128, 64, 16, 3, 1, 1, True),     # decoder3
+                                                         (4, 64, 32, 32, 3, 1, 1, True),      # decoder4
+                                                         (4, 32, 16, 64, 3, 1, 1, True),      # decoder5
+                                                         (64, 8, 128, 16, 3, 1, 1, False),    # MedT local stem (64 patches)
+                                                         (2, 16, 16, 128, 3, 1, 1, True)])    # LoGo decoderf
+def test_conv2d_gemm_matches_torch(n, ci, co, h, k, stride, pad, bias):
+    """medt_b200.shell_ops.conv2d (implicit-GEMM split-K kernels of csrc/conv_gemm.cu) against torch's fp32 convolution (TF32 off):
+    forward, dX, dW (and the bias path), in both modes: own forward + cuDNN backward (the default for the strided decoder1) and
+    own forward + own backward (MEDT_OWN_CONV=all)."""
+    from medt_b200.shell_ops import Conv2dGemm
+    torch.manual_seed(9)
+    conv = torch.nn.Conv2d(ci, co, k, stride=stride, padding=pad, bias=bias).cuda()
+    x = torch.randn(n, ci, h, h, device="cuda", requires_grad=True)
+    ref = conv(x)
+    d = torch.randn_like(ref)
+    gr = torch.autograd.grad(ref, [x, conv.weight] + ([conv.bias] if bias else []), d)
+    rel = lambda a, b: ((a - b).norm() / b.norm()).item()  # noqa: E731
+    for own_bwd in (False, True):
+        got = Conv2dGemm.apply(x, conv.weight, stride, pad, own_bwd)
+        if bias:
+            got = got + conv.bias.view(1, -1, 1, 1)
+        gg = torch.autograd.grad(got, [x, conv.weight] + ([conv.bias] if bias else []), d)
+        assert rel(got, ref) < 1e-5            # K = Ci*9 up to 2304 fp32 terms in a different order than cuDNN
+        for a, b in zip(gg, gr):
+            assert rel(a, b) < 2e-5            # dW sums up to 262 k positions in split slices (fp32 atomics)

@@ -1,0 +1,51 @@
+"""cuDNN fp32 vs the implicit-GEMM split-K kernels (csrc/conv_gemm.cu) on the conv shapes of the 128-px / 512-px steps:
+forward, dX, dW each timed with CUDA events (L2-warm, 20 reps).  One JSON line."""
+import json
+import os
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [REPO, os.path.join(REPO, "medical-transformer_b200")]
+import torch  # noqa: E402
+
+import medt_b200  # noqa: E402,F401  (TF32 off)
+from medt_b200.shell_ops import Conv2dGemm  # noqa: E402
+
+
+def conv2d(x, conv):
+    return Conv2dGemm.apply(x, conv.weight, int(conv.stride[0]), int(conv.padding[0]), True)
+
+torch.backends.cudnn.benchmark = True
+SHAPES = [("conv2 8->128 @64", 4, 8, 128, 64, 1), ("conv3 128->8 @64", 4, 128, 8, 64, 1), ("dec1 256->256 @8 s2", 4, 256, 256, 8, 2),
+          ("dec2 256->128 @8", 4, 256, 128, 8, 1), ("dec3 128->64 @16", 4, 128, 64, 16, 1), ("dec4 64->32 @32", 4, 64, 32, 32, 1),
+          ("dec5 32->16 @64", 4, 32, 16, 64, 1), ("512: conv2 @256", 4, 8, 128, 256, 1), ("512: conv3 @256", 4, 128, 8, 256, 1),
+          ("512: dec5 32->16 @256", 4, 32, 16, 256, 1)]
+
+
+def timeit(fn, reps=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps * 1e3
+
+
+res = {}
+for name, n, ci, co, h, s in SHAPES:
+    conv = torch.nn.Conv2d(ci, co, 3, stride=s, padding=1, bias=False).cuda()
+    x = torch.randn(n, ci, h, h, device="cuda", requires_grad=True)
+    r = {}
+    for tag, f in (("cudnn", lambda: conv(x)), ("own", lambda: conv2d(x, conv))):
+        y = f()
+        d = torch.randn_like(y)
+        r[tag + "_fwd_us"] = round(timeit(f), 1)
+        r[tag + "_bwd_us"] = round(timeit(lambda: torch.autograd.grad(f(), [x, conv.weight], d)) - r[tag + "_fwd_us"], 1)
+    flop = 2.0 * n * (h // s) ** 2 * co * ci * 9
+    r["own_fwd_tflops"] = round(flop / r["own_fwd_us"] / 1e6, 2)
+    res[name] = r
+print(json.dumps(res))
