@@ -13,6 +13,7 @@
  *   mt_up2x_relu_add_* <- relu(bilinear x2) + skip of the decoders
  *   mt_conv1x1_*       <- the bias-free 1x1 convolutions of the blocks
  *   mt_conv2d_*        <- the KxK convolutions of the stems and decoders
+ *   mt_head_ce_*       <- adjust(relu(x)) + F.cross_entropy, the tail of one training step (train.py:140,156)
  *
  * Conventions
  *   - plain C, no torch types; all pointers are DEVICE pointers unless named host_*;
@@ -160,6 +161,15 @@ int mt_conv2d_forward(int N, int Ci, int Co, int H, int W, int KH, int KW, int s
                       float* y, void* stream);
 int mt_conv2d_backward(int N, int Ci, int Co, int H, int W, int KH, int KW, int stride, int pad, const float* x, const float* w,
                        const float* dy, float* dx, float* dw, void* stream);
+
+/* The tail of a training step: logits = adjust(relu(x)) (1x1 conv with bias to TWO classes, axialnet.py:440,502 / :588,708) fused
+ * with loss = F.cross_entropy(logits, y) (metrics.py:17-20, train.py:156; mean over all pixels, labels in {0, 1}).
+ * x: (N,C,HW) pre-ReLU features, w: (2,C), b: (2), y: (N,HW) int64, logits: (N,2,HW) out, loss: 1 float, overwritten.
+ * backward: dloss (1 float, device) -> dx (N,C,HW; nullable), dw (2,C), db (2), all overwritten.  C <= 64. */
+int mt_head_ce_forward(int N, int C, int HW, const float* x, const float* w, const float* b, const long long* y, float* logits,
+                       float* loss, void* stream);
+int mt_head_ce_backward(int N, int C, int HW, const float* x, const float* w, const float* logits, const long long* y,
+                        const float* dloss, float* dx, float* dw, float* db, void* stream);
 
 /* Profiling hooks (bench.py roofline, ncu): launch only the stages selected by `stage_mask`
  * of a forward (bit 0 k_proj, 1 k_sim_stats, 2 k_attn, 3 k_out) or backward (bit 0

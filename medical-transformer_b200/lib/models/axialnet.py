@@ -243,7 +243,7 @@ class ResAxialAttentionUNet(_ShellBase):
         self.adjust = nn.Conv2d(int(128 * s), num_classes, kernel_size=1, stride=1, padding=0)
         self.soft = nn.Softmax(dim=1)        # constructed, never applied (reference :440,:502)
 
-    def _forward_impl(self, x):
+    def _forward_impl(self, x, features=False):
         x = self._stem(x, (self.conv1, self.conv2, self.conv3), (self.bn1, self.bn2, self.bn3))
         x1 = self.layer1(x)
         x2 = self.layer2(x1)
@@ -254,10 +254,14 @@ class ResAxialAttentionUNet(_ShellBase):
         x = _up_relu(self.decoder3, x, x2)
         x = _up_relu(self.decoder4, x, x1)
         x = _up_relu(self.decoder5, x)
-        return self.adjust(F.relu(x))
+        return x if features else self.adjust(F.relu(x))
 
     def forward(self, x):
         return self._forward_impl(x)
+
+    def forward_features(self, x):
+        """everything up to (not including) `self.adjust(F.relu(.))` -- medt_b200.TrainStep fuses that tail with the loss"""
+        return self._forward_impl(x, features=True)
 
 
 class medt_net(_ShellBase):
@@ -336,7 +340,7 @@ class medt_net(_ShellBase):
         c = xp.shape[1]
         return xp.reshape(GRID, GRID, n, c, PATCH, PATCH).permute(2, 3, 0, 4, 1, 5).reshape(n, c, side, side)
 
-    def _forward_impl(self, x):
+    def _forward_impl(self, x, features=False):
         xin = x
         # The global and the local branch are independent until the merge: the local branch runs on a
         # second CUDA stream (autograd replays its backward on that stream too), so the two chains of
@@ -361,7 +365,7 @@ class medt_net(_ShellBase):
         x_loc = x.clone()                       # outside the 128x128 patch grid x_loc stays == x (:658,:700)
         x_loc[:, :, :side_len, :side_len] = loc
         x = F.relu(conv2d(x + x_loc, self.decoderf))
-        return self.adjust(F.relu(x))
+        return x if features else self.adjust(F.relu(x))
 
     def _side_stream(self, device):
         # module-level cache keyed by (device, current stream): nn.DataParallel rebuilds its replicas on every forward, so
@@ -377,6 +381,10 @@ class medt_net(_ShellBase):
 
     def forward(self, x):
         return self._forward_impl(x)
+
+    def forward_features(self, x):
+        """everything up to (not including) `self.adjust(F.relu(.))` -- medt_b200.TrainStep fuses that tail with the loss"""
+        return self._forward_impl(x, features=True)
 
 
 # ----------------------------------------------------------------------------- factories

@@ -259,3 +259,49 @@ def conv2d(x, conv, with_bias=True):
     if with_bias and conv.bias is not None:
         y = y + conv.bias.view(1, -1, 1, 1)
     return y
+
+
+class HeadCE(torch.autograd.Function):
+    """loss = F.cross_entropy(adjust(relu(x)), y) for the two-class `adjust` 1x1 conv -- two kernels instead of ~10 ATen launches.
+    Returns (loss, logits); logits carry no gradient (they are a by-product for logging / thresholding)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, y):
+        _need_cuda(x, "head_ce")
+        lib = _cabi.load_library()
+        x = _cabi.dense(x)
+        n, c, h, w = x.shape
+        if weight.shape[0] != 2 or y.dtype != torch.int64:
+            raise ValueError("medt_b200.head_ce: two output classes and int64 labels expected")
+        y = y.contiguous()
+        w2 = weight.reshape(2, c).contiguous()
+        logits = torch.empty((n, 2, h, w), dtype=torch.float32, device=x.device)
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.mt_head_ce_forward(n, c, h * w, _p(x), _p(w2), _p(bias), _p(y), _p(logits), _p(loss), _stream(x.device))
+        _cabi.check(rc, "mt_head_ce_forward")
+        _cabi.LAUNCHES["kernels"] += 1
+        ctx.save_for_backward(x, w2, logits, y)
+        ctx.wshape = tuple(weight.shape)
+        ctx.mark_non_differentiable(logits)
+        return loss, logits
+
+    @staticmethod
+    def backward(ctx, dloss, _dlogits):
+        x, w2, logits, y = ctx.saved_tensors
+        lib = _cabi.load_library()
+        n, c, h, w = x.shape
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w2)
+        db = torch.empty(2, dtype=torch.float32, device=x.device)
+        dl = dloss.reshape(1).contiguous().float()
+        with torch.cuda.device(x.device):
+            rc = lib.mt_head_ce_backward(n, c, h * w, _p(x), _p(w2), _p(logits), _p(y), _p(dl), _p(dx), _p(dw), _p(db), _stream(x.device))
+        _cabi.check(rc, "mt_head_ce_backward")
+        _cabi.LAUNCHES["kernels"] += 1
+        return dx, dw.reshape(ctx.wshape), db, None
+
+
+def head_ce(x, adjust, y):
+    """(loss, logits) of `F.cross_entropy(adjust(F.relu(x)), y)`; `adjust` is the model's own nn.Conv2d(C, 2, 1) with bias."""
+    return HeadCE.apply(x, adjust.weight, adjust.bias, y)

@@ -148,7 +148,7 @@ class TrainStep:
         for p in self.model.parameters():
             p.grad = None
         state = {k: v.clone() for k, v in self.model.state_dict().items()}       # keep BN buffers untouched
-        loss = F.cross_entropy(self.model(self.x), self.y)
+        loss = self._loss()
         loss.backward()
         active = [p for p in self.model.parameters() if p.grad is not None]
         self.model.load_state_dict(state)
@@ -258,11 +258,23 @@ class TrainStep:
         """Call after flipping requires_grad (train.py:169-171) or changing lr."""
         self._build()
 
+    def _loss(self):
+        """forward + loss.  The tail `adjust(relu(x))` + cross-entropy runs as ONE fused kernel pair (csrc/head_ce.cu) when the
+        model exposes `forward_features` and a two-class 1x1 `adjust` with bias (every reference factory does); MEDT_NO_FUSED_HEAD=1
+        or any other model keeps `F.cross_entropy(model(x), y)`."""
+        m = self.model
+        adj = getattr(m, "adjust", None)
+        if (hasattr(m, "forward_features") and isinstance(adj, torch.nn.Conv2d) and adj.kernel_size == (1, 1) and adj.out_channels == 2
+                and adj.bias is not None and adj.in_channels <= 64 and not os.environ.get("MEDT_NO_FUSED_HEAD")):
+            from .shell_ops import head_ce
+            loss, _logits = head_ce(m.forward_features(self.x), adj, self.y)
+            return loss
+        return F.cross_entropy(m(self.x), self.y)              # LogNLLLoss == cross_entropy (metrics.py:17-20)
+
     def _step_body(self):
         for p in self.active:
             p.grad = None
-        out = self.model(self.x)
-        loss = F.cross_entropy(out, self.y)                    # LogNLLLoss == cross_entropy (metrics.py:17-20)
+        loss = self._loss()
         loss.backward()
         if self.flat_adam:
             for g in self.groups:

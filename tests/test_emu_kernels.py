@@ -172,6 +172,30 @@ def test_conv2d_gemm_kernels_under_emulation(emu_lib, n, ci, co, h, w, k, stride
         assert emu_lib.mt_conv2d_backward(n, ci, co, h, w, k, k, stride, pad, _ptr(xs), _ptr(ws), _ptr(_f32(d)), _ptr(dx), None, None) == 2
 
 
+@pytest.mark.parametrize("n,c,h,w", [(2, 16, 8, 8), (3, 5, 7, 9)])
+def test_head_ce_kernels_under_emulation(emu_lib, n, c, h, w):
+    """adjust(relu(x)) + cross-entropy (csrc/head_ce.cu) against torch: logits, loss, dx, dW, db"""
+    torch.manual_seed(6)
+    x = torch.randn(n, c, h, w, requires_grad=True)
+    wt = (torch.randn(2, c, 1, 1) * 0.5).requires_grad_(True)
+    b = torch.randn(2, requires_grad=True)
+    y = torch.randint(0, 2, (n, h, w))
+    logits = F.conv2d(F.relu(x), wt, b)
+    loss = F.cross_entropy(logits, y)
+    g = torch.autograd.grad(loss * 1.7, (x, wt, b))
+    xs, ws, bs = _f32(x), _f32(wt.reshape(2, c)), _f32(b)
+    ys = np.ascontiguousarray(y.numpy().astype(np.int64))
+    lg, ls = _f32(torch.zeros(n, 2, h, w)), _f32(torch.full((1,), 9.0))
+    assert emu_lib.mt_head_ce_forward(n, c, h * w, _ptr(xs), _ptr(ws), _ptr(bs), _ptr(ys), _ptr(lg), _ptr(ls), None) == 0
+    assert np.allclose(lg, logits.detach().numpy(), atol=1e-5) and abs(float(ls[0]) - loss.item()) < 1e-5
+    dx, dw, db = _f32(torch.full_like(x, 3.0)), _f32(torch.full((2, c), 3.0)), _f32(torch.full((2,), 3.0))
+    dl = _f32(torch.full((1,), 1.7))
+    assert emu_lib.mt_head_ce_backward(n, c, h * w, _ptr(xs), _ptr(ws), _ptr(lg), _ptr(ys), _ptr(dl), _ptr(dx), _ptr(dw), _ptr(db), None) == 0
+    assert np.allclose(dx, g[0].numpy(), atol=1e-6, rtol=1e-4)
+    assert np.allclose(dw, g[1].reshape(2, c).numpy(), atol=1e-6, rtol=1e-4)
+    assert np.allclose(db, g[2].numpy(), atol=1e-6, rtol=1e-4)
+
+
 def _golden_names():
     sys.path.insert(0, os.path.join(HERE, "golden"))
     sys.path.insert(0, HERE)

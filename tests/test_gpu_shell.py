@@ -152,3 +152,22 @@ def test_conv2d_gemm_matches_torch(n, ci, co, h, k, stride, pad, bias):
         assert rel(got, ref) < 1e-5            # K = Ci*9 up to 2304 fp32 terms in a different order than cuDNN
         for a, b in zip(gg, gr):
             assert rel(a, b) < 2e-5            # dW sums up to 262 k positions in split slices (fp32 atomics)
+
+
+@pytest.mark.parametrize("n,c,hw", [(4, 16, 128), (2, 16, 256), (3, 8, 33)])
+def test_head_ce_matches_torch(n, c, hw):
+    """medt_b200.shell_ops.head_ce == F.cross_entropy(adjust(F.relu(x)), y): loss, logits and every gradient"""
+    from medt_b200.shell_ops import head_ce
+    torch.manual_seed(2)
+    adjust = torch.nn.Conv2d(c, 2, 1).cuda()
+    x = torch.randn(n, c, hw, hw, device="cuda", requires_grad=True)
+    y = torch.randint(0, 2, (n, hw, hw), device="cuda")
+    logits = adjust(F.relu(x))
+    loss = F.cross_entropy(logits, y)
+    gr = torch.autograd.grad(loss, [x, adjust.weight, adjust.bias])
+    loss2, logits2 = head_ce(x, adjust, y)
+    gg = torch.autograd.grad(loss2, [x, adjust.weight, adjust.bias])
+    assert abs(loss2.item() - loss.item()) < 2e-6 * max(1.0, abs(loss.item()))
+    assert torch.allclose(logits2, logits, atol=1e-5, rtol=1e-5)
+    for a, b in zip(gg, gr):
+        assert ((a - b).norm() / b.norm()).item() < 2e-5
