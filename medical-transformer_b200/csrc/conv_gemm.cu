@@ -16,6 +16,7 @@
 // next chunk's global loads issued before the FMAs of the current one; gridDim.z slices of K accumulate with fp32 atomics into the
 // zero-initialised output (last-bit run-to-run differences, like cuDNN's own split-K algorithms).
 #include "common.cuh"
+#include "conv_tc.cuh"
 extern thread_local cudaError_t g_last_cuda;
 int mt_fail_msg(int code, const char* msg);
 cudaStream_t mt_side_fork(cudaStream_t main_stream);
@@ -214,7 +215,16 @@ static int cg_launch_gemm(const CgArgs& a, const float* img, const float* w, flo
   return 0;
 }
 
+static TcConv cg_tc_geom(const CgArgs& a) {
+  TcConv t{};
+  t.N = a.N; t.Cimg = a.Kimg; t.Crow = a.M; t.Hi = a.Hi; t.Wi = a.Wi; t.Ho = a.Ho; t.Wo = a.Wo; t.stride = a.stride; t.pad = a.pad;
+  t.KH = a.KH; t.KW = a.KW; t.KS = a.KS; t.K = a.K; t.dgrad = a.dgrad; t.Wm = a.Wm; t.P = a.P;
+  return t;
+}
+
 extern "C" {
+
+void mt_set_conv_tc(int mode) { tc_conv_set_mode(mode); }
 
 int mt_conv2d_forward(int N, int Ci, int Co, int H, int W, int KH, int KW, int stride, int pad, const float* x, const float* w,
                       float* y, void* stream) {
@@ -225,6 +235,11 @@ int mt_conv2d_forward(int N, int Ci, int Co, int H, int W, int KH, int KW, int s
   a.stride = stride; a.pad = pad; a.KH = KH; a.KW = KW; a.KS = KH * KW; a.K = Ci * a.KS; a.dgrad = 0; a.Wm = Co;
   a.P = (long)N * a.Ho * a.Wo;
   if (a.Ho <= 0 || a.Wo <= 0) return mt_fail_msg(MT_ERR_BAD_ARG, "mt_conv2d_forward: empty output");
+  {                                                               // tensor-core path (conv_tc.cu) where the shape is eligible
+    const int rc = tc_conv_fwd_or_dgrad(cg_tc_geom(a), x, w, y, (cudaStream_t)stream);
+    if (rc < 0) return mt_fail_msg(MT_ERR_CUDA, "mt_conv2d_forward: tcgen05 launch failed");
+    if (rc > 0) { g_last_cuda = cudaGetLastError(); return g_last_cuda == cudaSuccess ? MT_OK : mt_fail_msg(MT_ERR_CUDA, "mt_conv2d_forward: launch failed"); }
+  }
   if (cg_launch_gemm(a, x, w, y, (cudaStream_t)stream) != 0) return mt_fail_msg(MT_ERR_CUDA, "mt_conv2d_forward: memset failed");
   g_last_cuda = cudaGetLastError();
   return g_last_cuda == cudaSuccess ? MT_OK : mt_fail_msg(MT_ERR_CUDA, "mt_conv2d_forward: launch failed");
@@ -244,6 +259,9 @@ int mt_conv2d_backward(int N, int Ci, int Co, int H, int W, int KH, int KW, int 
     CgArgs a{};
     a.N = N; a.Kimg = Ci; a.M = Co; a.Hi = H; a.Wi = W; a.Ho = Ho; a.Wo = Wo; a.stride = stride; a.pad = pad; a.KH = KH; a.KW = KW;
     a.KS = KH * KW; a.K = Ci * a.KS; a.dgrad = 0; a.Wm = Co; a.P = (long)N * Ho * Wo;
+    const int rc = tc_conv_wgrad(cg_tc_geom(a), x, dy, dw, sd);
+    if (rc < 0) { mt_side_join(st, sd); return mt_fail_msg(MT_ERR_CUDA, "mt_conv2d_backward: tcgen05 wgrad launch failed"); }
+    if (rc == 0) {
     cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Co * a.K, sd);
     const int ty = Co <= 16 ? 4 : 16, BM = 4 * ty;
     const int gx = (a.K + 63) / 64, gy = (Co + BM - 1) / BM;
@@ -256,12 +274,15 @@ int mt_conv2d_backward(int N, int Ci, int Co, int H, int W, int KH, int KW, int 
     const dim3 grid(gx, gy, (unsigned)ps);
     if (ty == 4) k_conv_wgrad<4><<<grid, 64, 0, sd>>>(a, x, dy, dw, pper);
     else k_conv_wgrad<16><<<grid, 256, 0, sd>>>(a, x, dy, dw, pper);
+    }
   }
   if (dx) {
     CgArgs a{};                                                   // dX = conv(dY, flipped W^T), pad' = K - 1 - pad, stride 1
     a.N = N; a.Kimg = Co; a.M = Ci; a.Hi = Ho; a.Wi = Wo; a.Ho = H; a.Wo = W; a.stride = 1; a.pad = KH - 1 - pad; a.KH = KH; a.KW = KW;
     a.KS = KH * KW; a.K = Co * a.KS; a.dgrad = 1; a.Wm = Ci; a.P = (long)N * H * W;
-    if (cg_launch_gemm(a, dy, w, dx, st) != 0) { mt_side_join(st, sd); return mt_fail_msg(MT_ERR_CUDA, "mt_conv2d_backward: memset failed"); }
+    const int rc = tc_conv_fwd_or_dgrad(cg_tc_geom(a), dy, w, dx, st);
+    if (rc < 0) { mt_side_join(st, sd); return mt_fail_msg(MT_ERR_CUDA, "mt_conv2d_backward: tcgen05 dgrad launch failed"); }
+    if (rc == 0 && cg_launch_gemm(a, dy, w, dx, st) != 0) { mt_side_join(st, sd); return mt_fail_msg(MT_ERR_CUDA, "mt_conv2d_backward: memset failed"); }
   }
   mt_side_join(st, sd);
   g_last_cuda = cudaGetLastError();

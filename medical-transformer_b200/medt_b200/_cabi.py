@@ -46,7 +46,7 @@ EXPORTS = ["mt_version", "mt_last_error", "mt_last_launch_count", "mt_axial_save
            "mt_axial_bwd_workspace_bytes", "mt_axial_forward", "mt_axial_backward",
            "mt_axial_forward_stages", "mt_axial_backward_stages",
            "mt_up2x_relu_add_forward", "mt_up2x_relu_add_backward", "mt_bn_act_forward", "mt_bn_act_backward",
-           "mt_conv1x1_forward", "mt_conv1x1_backward", "mt_conv2d_forward", "mt_conv2d_backward", "mt_head_ce_forward", "mt_head_ce_backward"]
+           "mt_conv1x1_forward", "mt_conv1x1_backward", "mt_conv2d_forward", "mt_conv2d_backward", "mt_set_conv_tc", "mt_head_ce_forward", "mt_head_ce_backward"]
 
 
 def lib_path() -> str:
@@ -104,6 +104,8 @@ def load_library():
         lib.mt_conv2d_forward.argtypes = [I, I, I, I, I, I, I, I, I, VP, VP, VP, VP]
         lib.mt_conv2d_backward.restype = C.c_int
         lib.mt_conv2d_backward.argtypes = [I, I, I, I, I, I, I, I, I, VP, VP, VP, VP, VP, VP]
+        lib.mt_set_conv_tc.restype = None
+        lib.mt_set_conv_tc.argtypes = [I]
         lib.mt_head_ce_forward.restype = C.c_int
         lib.mt_head_ce_forward.argtypes = [I, I, I, VP, VP, VP, VP, VP, VP, VP]
         lib.mt_head_ce_backward.restype = C.c_int

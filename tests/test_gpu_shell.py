@@ -132,11 +132,23 @@ def test_misaligned_contiguous_views_give_the_same_result():
                                                          (4, 32, 16, 64, 3, 1, 1, True),      # decoder5
                                                          (64, 8, 128, 16, 3, 1, 1, False),    # MedT local stem (64 patches)
                                                          (2, 16, 16, 128, 3, 1, 1, True)])    # LoGo decoderf
-def test_conv2d_gemm_matches_torch(n, ci, co, h, k, stride, pad, bias):
-    """medt_b200.shell_ops.conv2d (implicit-GEMM split-K kernels of csrc/conv_gemm.cu) against torch's fp32 convolution (TF32 off):
-    forward, dX, dW (and the bias path), in both modes: own forward + cuDNN backward (the default for the strided decoder1) and
-    own forward + own backward (MEDT_OWN_CONV=all)."""
+@pytest.mark.parametrize("tc", [1, 0])
+def test_conv2d_gemm_matches_torch(n, ci, co, h, k, stride, pad, bias, tc):
+    """medt_b200.shell_ops.conv2d against torch's fp32 convolution (TF32 off): forward, dX, dW (and the bias path), own forward +
+    cuDNN backward and own forward + own backward -- on the tcgen05 3xTF32 tensor-core kernels (csrc/conv_tc.cu, tc = 1, the
+    default routing of mt_conv2d_*) and on the FMA-pipe split-K kernels (csrc/conv_gemm.cu, tc = 0).  The same fp32-grade tolerance
+    holds for both: the 3xTF32 split keeps the products at <= 2^-22 relative."""
+    from medt_b200 import _cabi
     from medt_b200.shell_ops import Conv2dGemm
+    lib = _cabi.load_library()
+    lib.mt_set_conv_tc(tc)
+    try:
+        _conv2d_case(Conv2dGemm, n, ci, co, h, k, stride, pad, bias)
+    finally:
+        lib.mt_set_conv_tc(1)
+
+
+def _conv2d_case(Conv2dGemm, n, ci, co, h, k, stride, pad, bias):
     torch.manual_seed(9)
     conv = torch.nn.Conv2d(ci, co, k, stride=stride, padding=pad, bias=bias).cuda()
     x = torch.randn(n, ci, h, h, device="cuda", requires_grad=True)

@@ -1,5 +1,6 @@
-"""cuDNN fp32 vs the implicit-GEMM split-K kernels (csrc/conv_gemm.cu) on the conv shapes of the 128-px / 512-px steps:
-forward, dX, dW each timed with CUDA events (L2-warm, 20 reps).  One JSON line."""
+"""cuDNN fp32 vs the own implicit-GEMM kernels on the conv shapes of the 128-px / 512-px steps: "tc" = tcgen05 3xTF32 tensor-core
+kernels (csrc/conv_tc.cu), "own" = FMA-pipe split-K kernels (csrc/conv_gemm.cu); forward and backward (dX + dW) timed with CUDA
+events (L2-warm, 20 reps).  One JSON line."""
 import json
 import os
 import sys
@@ -9,7 +10,10 @@ sys.path[:0] = [REPO, os.path.join(REPO, "medical-transformer_b200")]
 import torch  # noqa: E402
 
 import medt_b200  # noqa: E402,F401  (TF32 off)
+from medt_b200 import _cabi  # noqa: E402
 from medt_b200.shell_ops import Conv2dGemm  # noqa: E402
+
+LIB = _cabi.load_library()
 
 
 def conv2d(x, conv):
@@ -40,12 +44,14 @@ for name, n, ci, co, h, s in SHAPES:
     conv = torch.nn.Conv2d(ci, co, 3, stride=s, padding=1, bias=False).cuda()
     x = torch.randn(n, ci, h, h, device="cuda", requires_grad=True)
     r = {}
-    for tag, f in (("cudnn", lambda: conv(x)), ("own", lambda: conv2d(x, conv))):
+    for tag, f, tc in (("cudnn", lambda: conv(x), 1), ("own", lambda: conv2d(x, conv), 0), ("tc", lambda: conv2d(x, conv), 1)):
+        LIB.mt_set_conv_tc(tc)
         y = f()
         d = torch.randn_like(y)
         r[tag + "_fwd_us"] = round(timeit(f), 1)
         r[tag + "_bwd_us"] = round(timeit(lambda: torch.autograd.grad(f(), [x, conv.weight], d)) - r[tag + "_fwd_us"], 1)
     flop = 2.0 * n * (h // s) ** 2 * co * ci * 9
     r["own_fwd_tflops"] = round(flop / r["own_fwd_us"] / 1e6, 2)
+    r["tc_fwd_tflops"] = round(flop / r["tc_fwd_us"] / 1e6, 2)
     res[name] = r
 print(json.dumps(res))
