@@ -38,6 +38,9 @@ __device__ __forceinline__ bool tc_mbar_try(uint32_t bar, uint32_t parity) {
                : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ void tc_mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
 // bounded wait: a protocol error traps (the launch fails loudly) instead of hanging the GPU
 __device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity) {
   if (tc_mbar_try(bar, parity)) return;
@@ -79,6 +82,22 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Accuracy: the tensor core adds the products of one MMA to the fp32 accumulator with truncated alignment (measured: the error of
+// one long accumulation chain grows like sqrt(#MMAs) * 1e-7 of the result, 5 - 20x the FMA pipes' round-to-nearest chain).  The
+// MMAs are therefore dealt round-robin to NACC independent TMEM accumulators (all 512 columns: 4 at BN = 128 ... 16 at BN <= 32)
+// which the epilogue adds in fp32 with round-to-nearest: each chain is NACC times shorter and sqrt(NACC) times smaller.
+__host__ __device__ constexpr int tc_nacc(int bn) { return 512 / bn > 16 ? 16 : 512 / bn; }
+
+__device__ __forceinline__ void tc_ld16_sum(uint32_t taddr, int bn, int nacc, float (&acc)[16]) {
+  tc_ld16(taddr, acc);
+  for (int j = 1; j < nacc; ++j) {
+    float t[16];
+    tc_ld16(taddr + (uint32_t)(j * bn), t);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] += t[i];
+  }
+}
+
 // MODE 0: forward / dgrad (A = im2col rows, B = weights).  MODE 1: wgrad (A = im2col^T rows = taps, B = dy rows = channels).
 template <int MODE, int BN>
 __global__ void __launch_bounds__(256, 1)
@@ -87,7 +106,8 @@ k_conv_tc(const TcConv a, const float* __restrict__ img, const float* __restrict
   constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
   constexpr int TPR = 128 / BN;                              // B-loader threads per row
   constexpr int KPT = TC_KB / TPR;                           // reduction elements per B-loader thread and block (BN / 4)
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr int NACC = tc_nacc(BN);                          // independent TMEM accumulators, summed in fp32 by the epilogue
+  constexpr uint32_t TMEM_COLS = NACC * BN;
   constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   static_assert(KPT % 4 == 0 && KPT <= 32, "B tile split");
 
@@ -244,13 +264,17 @@ k_conv_tc(const TcConv a, const float* __restrict__ img, const float* __restrict
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t sA = tc_smem(tc_dyn + (size_t)stage * STAGE_BYTES), sB = sA + 2 * TC_A_BYTES;
+      const uint64_t ahi0 = tc_desc(sA, lboA, sboA), alo0 = tc_desc(sA + TC_A_BYTES, lboA, sboA);
+      const uint64_t bhi0 = tc_desc(sB, lboB, sboB), blo0 = tc_desc(sB + B_BYTES, lboB, sboB);
 #pragma unroll
-      for (int ks = 0; ks < TC_KB / 8; ++ks) {
-        const uint64_t ahi = tc_desc(sA + ks * 2 * 128 * 16, lboA, sboA), alo = tc_desc(sA + TC_A_BYTES + ks * 2 * 128 * 16, lboA, sboA);
-        const uint64_t bhi = tc_desc(sB + ks * 2 * BN * 16, lboB, sboB), blo = tc_desc(sB + B_BYTES + ks * 2 * BN * 16, lboB, sboB);
-        tc_mma_tf32(tmem, ahi, blo, IDESC, (it > 0 || ks > 0) ? 1u : 0u);
-        tc_mma_tf32(tmem, alo, bhi, IDESC, 1u);
-        tc_mma_tf32(tmem, ahi, bhi, IDESC, 1u);
+      for (int ks = 0; ks < TC_KB / 8; ++ks) {                  // the start-address field counts 16-byte units
+        const uint64_t ahi = ahi0 + (uint64_t)(ks * 2 * 128), alo = alo0 + (uint64_t)(ks * 2 * 128);
+        const uint64_t bhi = bhi0 + (uint64_t)(ks * 2 * BN), blo = blo0 + (uint64_t)(ks * 2 * BN);
+        const int step = it * (TC_KB / 8) + ks;
+        const uint32_t d = tmem + (uint32_t)((step % NACC) * BN);
+        tc_mma_tf32(d, ahi, blo, IDESC, step >= NACC ? 1u : 0u);
+        tc_mma_tf32(d, alo, bhi, IDESC, 1u);
+        tc_mma_tf32(d, ahi, bhi, IDESC, 1u);
       }
       tc_commit(tc_smem(&s_bar[stage]));
     }
@@ -279,9 +303,10 @@ k_conv_tc(const TcConv a, const float* __restrict__ img, const float* __restrict
       obase = (size_t)(okr ? row : 0);                                               // + co * K
     }
     const size_t cstride = MODE == 0 ? (size_t)HWo : (size_t)a.K;
+    const int nacc = min(NACC, nit * (TC_KB / 8));
     for (int c = (warp >> 2) * 16; c < BN; c += 32) {
       float acc[16];
-      tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, acc);
+      tc_ld16_sum(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, BN, nacc, acc);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int m = rowB0 + c + i;
@@ -295,6 +320,225 @@ k_conv_tc(const TcConv a, const float* __restrict__ img, const float* __restrict
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// 3x3 / stride 1 / pad 1 (every stem and decoder convolution but decoder1 and the 7x7 stem): the "slab" kernel.
+//
+// Output positions are numbered on the ZERO-PADDED grid of the whole batch, q = (n (H + 2) + oh) * Wp + ow with Wp = W + 2 (the two
+// extra columns per row and two extra rows per image are garbage rows of the tiles, dropped by the epilogue: H W / ((H + 2)(W + 2))
+// of the MMA rows are useful, and tiles run across image boundaries -- the 64 small patches of MedT's local branch pack densely).  Then tap (kh, kw) of position q reads
+// the padded input at q + kh * Wp + kw -- a CONSTANT row shift.  One CTA stages, per group of 8 input channels, the padded input
+// slab of its 128 positions plus halo ([channel / 4][R = 128 + 2 Wp + 2 rows][4 channels x 4 B], i.e. the K-major SWIZZLE_NONE
+// layout with 16-byte rows) ONCE, split into hi / lo, and issues the nine taps as nine MMAs whose A descriptors differ only in the
+// start address (+ (kh * Wp + kw) * 16 B): every input element is loaded, split and stored once and used by nine taps -- 9x less
+// gather work per MAC than the generic kernel above.  B = the 8 x 9 weights of the stage for the tile's BN output channels
+// ([tap][channel / 4][BN rows][16 B]).  Per stage: 27 tcgen05.mma (9 taps x 3 split terms) of 128 x BN x 8.
+// Register double buffering: the global loads of stage i + 2 are issued right after stage i's registers were stored, so a load has
+// two stages of MMA time to land.  dgrad = the same kernel on dy with the taps flipped and the weight matrix transposed.
+template <int BN>
+__global__ void __launch_bounds__(288, 1)
+k_conv_tc3(const TcConv a, const float* __restrict__ img, const float* __restrict__ wgt, float* __restrict__ out) {
+  constexpr int NACC = tc_nacc(BN);                           // independent TMEM accumulators, summed in fp32 by the epilogue
+  constexpr uint32_t TMEM_COLS = NACC * BN;
+  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr int B_HALF = 9 * 2 * BN * 16;                     // hi (or lo) weights of one stage
+  extern __shared__ __align__(128) unsigned char tc_dyn[];
+  __shared__ __align__(8) unsigned long long s_full[2], s_empty[2];
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = a.Hi, W = a.Wi, Wp = W + 2, HW = H * W, R = a.R;
+  const int PI = (H + 2) * Wp;                                // padded rows of one image (its own zero halo rows separate the images)
+  const int q0 = blockIdx.x * 128;                            // the tile's first row on the padded grid of the WHOLE batch
+  const int rowB0 = blockIdx.y * BN;
+  const int nst = a.Cimg >> 3;
+  const int st0 = blockIdx.z * a.kb_per, st1 = min(nst, st0 + a.kb_per);
+  const int A_HALF = 2 * R * 16;                              // hi (or lo) slab of one stage
+  const int STAGE = 2 * A_HALF + 2 * B_HALF;
+
+  if (tid == 0) {
+    tc_mbar_init(tc_smem(&s_full[0]), 256);                  // every loader thread arrives
+    tc_mbar_init(tc_smem(&s_full[1]), 256);
+    tc_mbar_init(tc_smem(&s_empty[0]), 1);                   // tcgen05.commit arrives
+    tc_mbar_init(tc_smem(&s_empty[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem(&s_tmem)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem;
+
+  // slab rows of this thread: padded index g = q0 + r -> input pixel (g / Wp - 1, g % Wp - 1), or -1 (zero padding / outside)
+  int off[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int r = tid + 256 * i;
+    const int g = q0 + r, n = g / PI, rem = g - n * PI, pa = rem / Wp, pb = rem - pa * Wp;
+    const int ih = pa - 1, iw = pb - 1;
+    off[i] = (r < R && n < a.N && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W) ? n * a.Cimg * HW + ih * W + iw : -1;
+  }
+  const float* imgn = img;
+  // weight task of this thread: output-channel row `brow`, channel quad `bc` of the stage
+  const bool hasB = tid < 2 * BN;
+  const int brow = tid % BN, bc = tid / BN;
+  const int bm = rowB0 + brow;
+  const bool okB = hasB && bm < a.Crow;
+
+  auto load_stage = [&](int s, float (&va)[24], float (&vb)[36]) {
+    const int c0 = s * 8;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float* src = imgn + (size_t)c0 * HW + (off[i] >= 0 ? off[i] : 0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) va[i * 8 + j] = off[i] >= 0 ? __ldg(src + (size_t)j * HW) : 0.f;
+    }
+    if (okB) {
+      if (!a.dgrad) {                                         // W[co = bm][c0 + 4 bc .. + 4][9]: 36 contiguous floats, 16-byte aligned
+        const float4* src = reinterpret_cast<const float4*>(wgt + ((size_t)bm * a.Cimg + c0 + 4 * bc) * 9);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          const float4 t = __ldg(src + i);
+          vb[4 * i] = t.x; vb[4 * i + 1] = t.y; vb[4 * i + 2] = t.z; vb[4 * i + 3] = t.w;
+        }
+      } else {                                                // W[co = c0 + 4 bc + e][ci = bm][9], taps flipped at store time
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float* src = wgt + ((size_t)(c0 + 4 * bc + e) * a.Wm + bm) * 9;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) vb[e * 9 + t] = __ldg(src + t);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 36; ++i) vb[i] = 0.f;
+    }
+  };
+
+  auto store_stage = [&](int buf, const float (&va)[24], const float (&vb)[36]) {
+    unsigned char* st = tc_dyn + (size_t)buf * STAGE;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int r = tid + 256 * i;
+      if (r < R) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float4 h, l;
+          tc_split(va[i * 8 + 4 * c + 0], h.x, l.x); tc_split(va[i * 8 + 4 * c + 1], h.y, l.y);
+          tc_split(va[i * 8 + 4 * c + 2], h.z, l.z); tc_split(va[i * 8 + 4 * c + 3], h.w, l.w);
+          reinterpret_cast<float4*>(st)[c * R + r] = h;
+          reinterpret_cast<float4*>(st + A_HALF)[c * R + r] = l;
+        }
+      }
+    }
+    if (hasB) {
+      float4* bh = reinterpret_cast<float4*>(st + 2 * A_HALF);
+      float4* bl = reinterpret_cast<float4*>(st + 2 * A_HALF + B_HALF);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        float4 h, l;
+        float x0, x1, x2, x3;
+        if (a.dgrad) { x0 = vb[8 - t]; x1 = vb[9 + 8 - t]; x2 = vb[18 + 8 - t]; x3 = vb[27 + 8 - t]; }
+        else { x0 = vb[t]; x1 = vb[9 + t]; x2 = vb[18 + t]; x3 = vb[27 + t]; }
+        tc_split(x0, h.x, l.x); tc_split(x1, h.y, l.y); tc_split(x2, h.z, l.z); tc_split(x3, h.w, l.w);
+        bh[(t * 2 + bc) * BN + brow] = h;
+        bl[(t * 2 + bc) * BN + brow] = l;
+      }
+    }
+  };
+
+  // loader side of one stage: wait until the MMAs that read this buffer have retired, store, publish to the async proxy, arrive
+  auto run_stage = [&](int it, const float (&va)[24], const float (&vb)[36]) {
+    const int buf = a.nbuf == 2 ? (it & 1) : 0;
+    const int use = a.nbuf == 2 ? (it >> 1) : it;             // how often this buffer was filled before
+    if (use >= 1) tc_mbar_wait(tc_smem(&s_empty[buf]), (uint32_t)((use - 1) & 1));
+    store_stage(buf, va, vb);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_mbar_arrive(tc_smem(&s_full[buf]));
+  };
+
+  const int nit = st1 - st0;
+  if (warp < 8) {
+    // ===== loader warps: registers double-buffered two stages ahead, shared memory double-buffered against the tensor core
+    float va0[24], vb0[36], va1[24], vb1[36];
+    if (nit > 0) load_stage(st0, va0, vb0);
+    if (nit > 1) load_stage(st0 + 1, va1, vb1);
+    for (int it = 0; it < nit; it += 2) {
+      run_stage(it, va0, vb0);
+      if (it + 2 < nit) load_stage(st0 + it + 2, va0, vb0);
+      if (it + 1 < nit) {
+        run_stage(it + 1, va1, vb1);
+        if (it + 3 < nit) load_stage(st0 + it + 3, va1, vb1);
+      }
+    }
+  } else if (lane == 0) {
+    // ===== MMA issuer (one thread): 27 tcgen05.mma per stage, descriptors = base + constant row / tap offsets
+    const uint32_t lboA = (uint32_t)R * 16u, lboB = (uint32_t)BN * 16u;
+    for (int it = 0; it < nit; ++it) {
+      const int buf = a.nbuf == 2 ? (it & 1) : 0;
+      const int use = a.nbuf == 2 ? (it >> 1) : it;
+      tc_mbar_wait(tc_smem(&s_full[buf]), (uint32_t)(use & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sA = tc_smem(tc_dyn + (size_t)buf * STAGE), sB = sA + 2 * A_HALF;
+      const uint64_t ahi0 = tc_desc(sA, lboA, 128u), alo0 = tc_desc(sA + A_HALF, lboA, 128u);
+      const uint64_t bhi0 = tc_desc(sB, lboB, 128u), blo0 = tc_desc(sB + B_HALF, lboB, 128u);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int kh = t / 3, kw = t - kh * 3;
+        const uint64_t sh = (uint64_t)(uint32_t)(kh * Wp + kw);           // start-address field counts 16-byte units = slab rows
+        const uint64_t tb = (uint64_t)(uint32_t)(t * 2 * BN);
+        const int step = it * 9 + t;
+        const uint32_t d = tmem + (uint32_t)((step % NACC) * BN);
+        tc_mma_tf32(d, ahi0 + sh, blo0 + tb, IDESC, step >= NACC ? 1u : 0u);
+        tc_mma_tf32(d, alo0 + sh, bhi0 + tb, IDESC, 1u);
+        tc_mma_tf32(d, ahi0 + sh, bhi0 + tb, IDESC, 1u);
+      }
+      tc_commit(tc_smem(&s_empty[buf]));                      // frees the buffer; the last one also tells the epilogue
+    }
+  }
+
+  if (nit > 0 && warp < 8) {
+    const int last = nit - 1;
+    const int buf = a.nbuf == 2 ? (last & 1) : 0, use = a.nbuf == 2 ? (last >> 1) : last;
+    tc_mbar_wait(tc_smem(&s_empty[buf]), (uint32_t)(use & 1));               // a commit covers every earlier MMA
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;
+    const int g = q0 + q * 32 + lane, n = g / PI, rem = g - n * PI, oh = rem / Wp, ow = rem - oh * Wp;
+    const bool okr = n < a.N && ow < W && oh < H;
+    float* obase = out + (okr ? (size_t)n * a.Crow * HW + oh * W + ow : 0);
+    const int nacc = min(NACC, nit * 9);
+    for (int c = (warp >> 2) * 16; c < BN; c += 32) {
+      float acc[16];
+      tc_ld16_sum(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, BN, nacc, acc);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int m = rowB0 + c + i;
+        if (okr && m < a.Crow) {
+          float* dst = obase + (size_t)m * HW;
+          if (a.atomic) atomicAdd(dst, acc[i]); else *dst = acc[i];
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+}
+
+template <int BN>
+int tc3_launch_bn(const TcConv& a, dim3 grid, int smem, const float* img, const float* w, float* out, cudaStream_t st) {
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    if (cudaFuncSetAttribute(k_conv_tc3<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+    attr_smem = smem;
+  }
+  k_conv_tc3<BN><<<grid, 288, smem, st>>>(a, img, w, out);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 int g_tc_mode = -1;
@@ -341,6 +585,48 @@ int tc_launch(TcConv a, const float* img, const float* mat, float* out, size_t o
   }
 }
 
+int tc3_launch(TcConv a, const float* img, const float* w, float* out, cudaStream_t st) {
+  int dev = 0, nsm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  const int Wp = a.Wi + 2;
+  a.R = 128 + 2 * Wp + 2;
+  a.tiles_per_img = 0;
+  const long prow = (long)a.N * (a.Hi + 2) * Wp;                   // rows of the batch's padded grid
+  if (prow + a.R > 0x7fffffffL) return 0;
+  int bn = a.Crow <= 16 ? 16 : a.Crow <= 32 ? 32 : a.Crow <= 64 ? 64 : 128;
+  {
+    static int min_bn = -1;                                        // MT_TC_MIN_BN: bring-up knob (N = 16 vs 32 accumulation accuracy)
+    if (min_bn < 0) { const char* e = getenv("MT_TC_MIN_BN"); min_bn = e ? atoi(e) : 16; }
+    if (bn < min_bn) bn = min_bn <= 32 ? 32 : min_bn <= 64 ? 64 : 128;
+  }
+  const int nst = a.Cimg / 8;
+  auto stage_bytes = [&](int b) { return 64 * a.R + 576 * b; };
+  a.nbuf = nst > 1 ? 2 : 1;
+  if (a.nbuf * stage_bytes(bn) > 220 * 1024 && bn == 128) bn = 64;           // wide rows: narrower channel tile instead of one buffer
+  if (a.nbuf * stage_bytes(bn) > 220 * 1024) a.nbuf = 1;
+  if (stage_bytes(bn) > 220 * 1024) return 0;
+  const long gx = (prow + 127) / 128;
+  const int gy = (a.Crow + bn - 1) / bn;
+  long ks = ((long)nsm + gx * gy - 1) / (gx * gy);
+  const long ks_max = (nst + 1) / 2;                               // at least two stages per slice
+  if (ks > ks_max) ks = ks_max;
+  if (ks < 1) ks = 1;
+  a.kb_per = (int)((nst + ks - 1) / ks);
+  ks = (nst + a.kb_per - 1) / a.kb_per;
+  a.atomic = ks > 1;
+  if (gx > 0x7fffffffL || gy > 65535 || ks > 65535) return 0;
+  if (a.atomic && cudaMemsetAsync(out, 0, sizeof(float) * (size_t)a.P * a.Crow, st) != cudaSuccess) return -1;
+  const dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)ks);
+  const int smem = a.nbuf * stage_bytes(bn);
+  switch (bn) {
+    case 16: return tc3_launch_bn<16>(a, grid, smem, img, w, out, st);
+    case 32: return tc3_launch_bn<32>(a, grid, smem, img, w, out, st);
+    case 64: return tc3_launch_bn<64>(a, grid, smem, img, w, out, st);
+    default: return tc3_launch_bn<128>(a, grid, smem, img, w, out, st);
+  }
+}
+
 int ilog2_exact(int v) {
   if (v <= 0 || (v & (v - 1))) return -1;
   int l = 0;
@@ -366,6 +652,11 @@ int tc_conv_fwd_or_dgrad(const TcConv& geom, const float* img, const float* w, f
   if (a.KH > 8 || a.KW > 8 || a.P <= 0 || a.P > 0x7fffffffL) return 0;
   if ((long)a.N * a.Cimg * a.Hi * a.Wi > 0x7fffffffL) return 0;              // 32-bit gather offsets
   a.rowsA = (int)a.P; a.rowsB = a.Crow; a.kdim = a.K; a.lgWo = a.lgHWo = 0;
+  if (a.KH == 3 && a.KW == 3 && a.stride == 1 && a.pad == 1 && a.Cimg % 8 == 0 && a.Wi <= 256 && a.Ho == a.Hi && a.Wo == a.Wi &&
+      ((uintptr_t)w & 15) == 0) {
+    const int rc = tc3_launch(a, img, w, out, st);
+    if (rc != 0) return rc;
+  }
   return tc_launch<0>(a, img, w, out, (size_t)a.P * a.Crow, st);
 }
 

@@ -14,6 +14,7 @@ struct TcConv {
   int kb_per;                                                       // k blocks (of 32) per gridDim.z slice
   int atomic;                                                       // epilogue accumulates with fp32 atomics (split-K)
   int dbg;                                                          // bit 0: swap LBO / SBO in the smem descriptors (bring-up)
+  int R, tiles_per_img, nbuf;                                       // slab kernel (3x3 / stride 1): slab rows, tiles per image, smem buffers
 };
 
 // 1 = launched, 0 = shape not eligible (caller uses the FMA kernels), < 0 = CUDA error.  `out` must be zeroed by the caller when the

@@ -10,6 +10,8 @@
 // one CTA per (group, channel) for the reductions.
 #include <stdio.h>
 #include "common.cuh"
+#include "bn_cluster.cuh"
+#include <cstdlib>
 
 // ---------------------------------------------------------------------------------------------
 // bilinear x2, align_corners=False:  src = dst/2 - 0.25 clamped at 0
@@ -125,10 +127,6 @@ k_up2x_bwd(int planes, int C, int H, int W, const float* __restrict__ dout, cons
 
 // ---------------------------------------------------------------------------------------------
 // BatchNorm2d (+residual)(+ReLU), one CTA per (channel, statistic group)
-struct BnActArgs {
-  int N, C, HW, G, training, relu;
-  float eps, momentum;
-};
 
 __device__ __forceinline__ float2 block_sum2(float a, float b) {
   __shared__ float ra[32], rb[32];
@@ -348,6 +346,13 @@ k_bn_act_bwd(BnActArgs a, const float* __restrict__ x, const float* __restrict__
 extern thread_local cudaError_t g_last_cuda;
 int mt_fail_msg(int code, const char* msg);
 
+// MT_BN_CLUSTER=0 keeps the one-CTA-per-channel kernels (A/B runs)
+static int bn_cluster_mode() {
+  static int mode = -1;
+  if (mode < 0) { const char* e = getenv("MT_BN_CLUSTER"); mode = e ? (atoi(e) != 0) : 1; }
+  return mode;
+}
+
 extern "C" {
 
 int mt_up2x_relu_add_forward(int planes, int C, int H, int W, const float* in, const float* bias, const float* skip,
@@ -384,7 +389,13 @@ int mt_bn_act_forward(int N, int C, int HW, int groups, int training, int relu, 
   const bool vec = HW % 4 == 0 && mt_al16(x) && mt_al16(y) && mt_al16(residual);   // else the scalar kernels
   const int cnt = (N / groups) * HW / (vec ? 4 : 1);
   const int bs = cnt >= 1024 ? 256 : (cnt >= 256 ? 128 : 64);
-  if (vec)
+  int clustered = 0;
+  if (vec && bn_cluster_mode()) {                        // a thread-block cluster per channel (bn_cluster.cu)
+    clustered = bn_cluster_forward(a, x, residual, gamma, beta, running_mean, running_var, y, save_mean, save_invstd, (cudaStream_t)stream);
+    if (clustered < 0) return mt_fail_msg(MT_ERR_CUDA, "mt_bn_act_forward: cluster launch failed");
+  }
+  if (clustered) {
+  } else if (vec)
     k_bn_act_fwd<true><<<dim3(C, groups), bs, 0, (cudaStream_t)stream>>>(a, x, residual, gamma, beta, running_mean,
                                                                            running_var, y, save_mean, save_invstd);
   else
@@ -410,7 +421,13 @@ int mt_bn_act_backward(int N, int C, int HW, int groups, int training, int relu,
   const bool vec = HW % 4 == 0 && mt_al16(x) && mt_al16(y) && mt_al16(dy) && mt_al16(dx) && mt_al16(dresidual);
   const int cnt = (N / groups) * HW / (vec ? 4 : 1);
   const int bs = cnt >= 1024 ? 256 : (cnt >= 256 ? 128 : 64);
-  if (vec)
+  int clustered = 0;
+  if (vec && bn_cluster_mode()) {
+    clustered = bn_cluster_backward(a, x, y, dy, gamma, save_mean, save_invstd, dx, dresidual, dgamma, dbeta, (cudaStream_t)stream);
+    if (clustered < 0) return mt_fail_msg(MT_ERR_CUDA, "mt_bn_act_backward: cluster launch failed");
+  }
+  if (clustered) {
+  } else if (vec)
     k_bn_act_bwd<true><<<dim3(C, groups), bs, 0, (cudaStream_t)stream>>>(a, x, y, dy, gamma, save_mean, save_invstd, dx,
                                                                            dresidual, dgamma, dbeta);
   else

@@ -193,15 +193,16 @@ def conv1x1(x, conv, relu_in=False):
 
 
 class Conv2dGemm(torch.autograd.Function):
-    """KxK convolution on the implicit-GEMM split-K kernels of csrc/conv_gemm.cu.  `own_bwd`: dX (stride 1 only) and dW on the
-    same kernels; otherwise the backward is cuDNN's (torch.ops.aten.convolution_backward)."""
+    """KxK convolution through mt_conv2d_* (tcgen05 3xTF32 tensor-core kernels of csrc/conv_tc.cu where the shape is eligible, the
+    FMA-pipe split-K kernels of csrc/conv_gemm.cu otherwise).  `own_bwd`: 0 / False = the backward is cuDNN's
+    (torch.ops.aten.convolution_backward), 1 / True = dX (stride 1 only) and dW on the own kernels, 2 = own dX, cuDNN dW."""
 
     @staticmethod
     def forward(ctx, x, weight, stride, pad, own_bwd):
         _need_cuda(x, "conv2d")
         lib = _cabi.load_library()
         x = _cabi.dense(x)
-        weight = weight.contiguous()
+        weight = _cabi.dense(weight)
         n, ci, h, w = x.shape
         co, _, kh, kw = weight.shape
         ho, wo = (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1
@@ -211,7 +212,7 @@ class Conv2dGemm(torch.autograd.Function):
         _cabi.check(rc, "mt_conv2d_forward")
         _cabi.LAUNCHES["kernels"] += 1
         ctx.save_for_backward(x, weight)
-        ctx.stride, ctx.pad, ctx.own_bwd = stride, pad, bool(own_bwd)
+        ctx.stride, ctx.pad, ctx.own_bwd = stride, pad, int(own_bwd)
         return y
 
     @staticmethod
@@ -221,41 +222,60 @@ class Conv2dGemm(torch.autograd.Function):
         n, ci, h, w = x.shape
         co, _, kh, kw = weight.shape
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+
+        def cudnn(mask_dx, mask_dw):
+            return torch.ops.aten.convolution_backward(dy, x, weight, None, [ctx.stride] * 2, [ctx.pad] * 2, [1, 1], False, [0, 0], 1,
+                                                       [bool(mask_dx), bool(mask_dw), False])
         if not ctx.own_bwd:
-            dx, dw, _ = torch.ops.aten.convolution_backward(dy, x, weight, None, [ctx.stride] * 2, [ctx.pad] * 2, [1, 1], False, [0, 0], 1,
-                                                            [bool(need_dx), bool(need_dw), False])
+            dx, dw, _ = cudnn(need_dx, need_dw)
             return dx, dw, None, None, None
         lib = _cabi.load_library()
         own_dx = need_dx and ctx.stride == 1
+        own_dw = need_dw and ctx.own_bwd == 1
         dx = torch.empty_like(x) if own_dx else None
-        dw = torch.empty_like(weight) if need_dw else None
-        if own_dx or need_dw:
+        dw = torch.empty_like(weight) if own_dw else None
+        if own_dx or own_dw:
             with torch.cuda.device(x.device):
                 rc = lib.mt_conv2d_backward(n, ci, co, h, w, kh, kw, ctx.stride, ctx.pad, _p(x), _p(weight), _p(dy), _p(dx), _p(dw),
                                             _stream(x.device))
             _cabi.check(rc, "mt_conv2d_backward")
-            _cabi.LAUNCHES["kernels"] += (1 if own_dx else 0) + (1 if need_dw else 0)
-        if need_dx and not own_dx:
-            dx = torch.ops.aten.convolution_backward(dy, x, weight, None, [ctx.stride] * 2, [ctx.pad] * 2, [1, 1], False, [0, 0], 1,
-                                                     [True, False, False])[0]
+            _cabi.LAUNCHES["kernels"] += (1 if own_dx else 0) + (1 if own_dw else 0)
+        rest_dx, rest_dw = need_dx and not own_dx, need_dw and not own_dw
+        if rest_dx or rest_dw:
+            gx, gw, _ = cudnn(rest_dx, rest_dw)
+            dx = gx if rest_dx else dx
+            dw = gw if rest_dw else dw
         return dx, dw, None, None, None
 
 
 def conv2d(x, conv, with_bias=True):
-    """`conv` is the module's own nn.Conv2d (weight used in place).  Measured on B200 (tools/time_convs.py, profiles/r2_notes.md):
-    cuDNN's fp32 algorithms win on the stride-1 3x3 shapes of this network (15 - 27 TFLOP/s against 5 - 20 for the generic
-    implicit-GEMM kernel) but collapse on decoder1 (256 -> 256, stride 2, 8x8 -> 4x4: 16 CTAs, 105 - 172 us): that forward runs
-    on csrc/conv_gemm.cu (27 us, split-K over all SMs), everything else stays cuDNN (north_star: "the conv stem/decoder and
-    adjust blocks are cuDNN").  MEDT_OWN_CONV=all routes every eligible convolution (forward and backward) through the own
-    kernels, MEDT_OWN_CONV=none none."""
+    """`conv` is the module's own nn.Conv2d (weight used in place).  Routing (MEDT_OWN_CONV; measured on B200 with
+    tools/time_convs.py, profiles/r2_notes.md):
+      "tc" (default)  the 3x3 / stride-1 / pad-1 convolutions with Ci % 8 == 0 (every stem / decoder convolution but the 7x7 stem
+                      and decoder1) run forward and dX on the tcgen05 3xTF32 slab kernel (csrc/conv_tc.cu); dW by MEDT_OWN_WGRAD
+                      (default cuDNN); decoder1 (stride 2: cuDNN's fp32 forward collapses to 16 CTAs) runs its forward on the own
+                      kernels and its backward on cuDNN;
+      "strided"       only decoder1's forward on the own kernels (the round-2a policy);
+      "all"           every eligible convolution forward + dX + dW on the own kernels;   "none"  cuDNN everywhere."""
     k = conv.kernel_size
-    mode = os.environ.get("MEDT_OWN_CONV", "strided")
+    mode = os.environ.get("MEDT_OWN_CONV", "tc")
     ok = (k[0] == k[1] and conv.stride[0] == conv.stride[1] and isinstance(conv.padding, tuple) and conv.padding[0] == conv.padding[1]
           and conv.dilation == (1, 1) and conv.groups == 1 and conv.padding_mode == "zeros" and x.is_cuda and x.dtype == torch.float32
-          and mode != "none" and (mode == "all" or (conv.stride[0] > 1 and k[0] == 3)))
+          and mode != "none")
+    strided3 = ok and conv.stride[0] > 1 and k[0] == 3
+    slab = (ok and k[0] == 3 and conv.stride[0] == 1 and conv.padding[0] == 1 and conv.in_channels % 8 == 0 and x.shape[-1] <= 256)
+    if mode == "all":
+        bwd = 1
+    elif mode == "tc" and slab:
+        bwd = 1 if os.environ.get("MEDT_OWN_WGRAD") else 2
+    elif mode in ("tc", "strided") and strided3:
+        bwd = 0
+    else:
+        ok = ok and mode == "all"
+        bwd = 0
     if not ok:
         return F.conv2d(x, conv.weight, conv.bias if with_bias else None, conv.stride, conv.padding, conv.dilation, conv.groups)
-    y = Conv2dGemm.apply(x, conv.weight, int(conv.stride[0]), int(conv.padding[0]), mode == "all")
+    y = Conv2dGemm.apply(x, conv.weight, int(conv.stride[0]), int(conv.padding[0]), bwd)
     if with_bias and conv.bias is not None:
         y = y + conv.bias.view(1, -1, 1, 1)
     return y

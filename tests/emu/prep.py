@@ -145,6 +145,13 @@ int tc_conv_fwd_or_dgrad(const TcConv&, const float*, const float*, float*, cuda
 int tc_conv_wgrad(const TcConv&, const float*, const float*, float*, cudaStream_t) { return 0; }
 int tc_conv_mode() { return g_mode; }
 void tc_conv_set_mode(int m) { g_mode = m; }
+''',
+                     # thread-block clusters / distributed shared memory: not emulated, the one-CTA-per-channel kernels run instead
+                     "bn_cluster.cu": '''#include "bn_cluster.cuh"
+int bn_cluster_forward(const BnActArgs&, const float*, const float*, const float*, const float*, float*, float*, float*, float*, float*,
+                       cudaStream_t) { return 0; }
+int bn_cluster_backward(const BnActArgs&, const float*, const float*, const float*, const float*, const float*, const float*, float*,
+                        float*, float*, float*, cudaStream_t) { return 0; }
 '''}
 
 
