@@ -112,6 +112,81 @@ def _all_reduce_mean_(t, world, pg):
             t.div_(world)
 
 
+class EarlyBucket:
+    """Two-bucket mean all-reduce of one FlatGroup's gradient with the FIRST bucket overlapped with the rest of backward.
+
+    The group's parameters are laid out in gradient-arrival order (TrainStep probes it): the first `k` of them -- the prefix that
+    holds >= `frac` of the elements: adjust, the decoders and the deep layers, whose gradients are complete when backward has
+    not yet reached layer3 -- are gathered into the flat gradient and all-reduced on a forked stream the moment the last of them
+    received its gradient (post-accumulate-grad hooks count arrivals); the small remainder (layer1 / layer2 / stem) is gathered
+    and reduced after backward, then the forked stream is joined.  Inside a CUDA-graph capture the fork / join become graph
+    edges, so the NCCL kernel of the first bucket runs next to the attention backward kernels.  Device agnostic: without CUDA
+    (the gloo CPU test) both reductions run in line at the same points of the step."""
+
+    def __init__(self, group, world, pg, frac=0.85):
+        self.g, self.world, self.pg = group, world, pg
+        total = sum(p.numel() for p in group.params)
+        acc, k = 0, 0
+        while k < len(group.params) and acc < frac * total and group.params[k].numel() % 4 == 0:
+            acc += group.params[k].numel()
+            k += 1
+        self.k, self.n_early = k, acc
+        dev = group.flat.device
+        self.stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        self.armed, self.count, self.fired = False, 0, False
+        self.handles = [p.register_post_accumulate_grad_hook(self._hook) for p in group.params[:k]]
+
+    def remove(self):
+        for h in self.handles:
+            h.remove()
+        self.handles = []
+
+    def arm(self):
+        self.armed, self.count, self.fired = True, 0, False
+
+    def _hook(self, _p):
+        if not self.armed:
+            return
+        self.count += 1
+        if self.count == self.k:
+            self._fire()
+
+    def _copy(self, lo, hi):
+        g = self.g
+        if hi > lo:
+            if hasattr(torch, "_foreach_copy_"):
+                torch._foreach_copy_(g.grad_views[lo:hi], [p.grad for p in g.params[lo:hi]])
+            else:
+                for v, p in zip(g.grad_views[lo:hi], g.params[lo:hi]):
+                    v.copy_(p.grad)
+
+    def _fire(self):
+        self._copy(0, self.k)
+        early = self.g.flat.grad[:self.n_early]
+        if self.stream is not None:
+            cur = torch.cuda.current_stream(early.device)
+            self.stream.wait_stream(cur)
+            with torch.cuda.stream(self.stream):
+                _all_reduce_mean_(early, self.world, self.pg)
+        else:
+            _all_reduce_mean_(early, self.world, self.pg)
+        self.fired = True
+
+    def finish(self):
+        """after backward: the second bucket, then join the first"""
+        self.armed = False
+        g = self.g
+        if not self.fired:                     # a prefix parameter received no gradient this step: one plain reduction
+            g.gather_grads_()
+            _all_reduce_mean_(g.flat.grad, self.world, self.pg)
+            return
+        self._copy(self.k, len(g.params))
+        if self.n_early < g.flat.grad.numel():
+            _all_reduce_mean_(g.flat.grad[self.n_early:], self.world, self.pg)
+        if self.stream is not None:
+            torch.cuda.current_stream(g.flat.device).wait_stream(self.stream)
+
+
 class TrainStep:
     def __init__(self, model, batch_shape, lr=1e-3, weight_decay=1e-5, device=None, use_graph=True,
                  process_group=None, loss_slots=64, flat_adam=None):
@@ -140,6 +215,8 @@ class TrainStep:
             flat_adam = not os.environ.get("MEDT_NO_FLAT_ADAM")
         self.flat_adam = bool(flat_adam)
         self.groups = []
+        self._early = None
+        self._arrival = {}
         self._build()
 
     # ------------------------------------------------------------------ setup
@@ -148,8 +225,15 @@ class TrainStep:
         for p in self.model.parameters():
             p.grad = None
         state = {k: v.clone() for k, v in self.model.state_dict().items()}       # keep BN buffers untouched
+        order, hooks = [], []
+        for p in self.model.parameters():
+            if p.requires_grad:
+                hooks.append(p.register_post_accumulate_grad_hook(lambda q, _o=order: _o.append(id(q))))
         loss = self._loss()
         loss.backward()
+        for h in hooks:
+            h.remove()
+        self._arrival = {pid: i for i, pid in enumerate(order)}                  # gradient arrival order (EarlyBucket layout)
         active = [p for p in self.model.parameters() if p.grad is not None]
         self.model.load_state_dict(state)
         for p in self.model.parameters():
@@ -167,7 +251,11 @@ class TrainStep:
         act = {id(p) for p in self.active}
         if not grouped <= act:
             self.groups, self.opt, grouped = [], None, set()
+            if self._early is not None:
+                self._early.remove()
+                self._early = None
         fresh = [p for p in self.active if id(p) not in grouped]
+        fresh.sort(key=lambda p: self._arrival.get(id(p), 1 << 30))              # early gradients first (stable inside FlatGroup)
         if fresh:
             g = FlatGroup(fresh)
             self.groups.append(g)
@@ -177,6 +265,8 @@ class TrainStep:
                 self.opt.param_groups[0]["params"].append(g.flat)
         for pg in self.opt.param_groups:
             pg["lr"], pg["weight_decay"] = self.lr, self.weight_decay
+        if self.world > 1 and self._early is None and self.groups and not os.environ.get("MEDT_NO_OVERLAP_REDUCE"):
+            self._early = EarlyBucket(self.groups[0], self.world, self.pg)
 
     def _build(self):
         self.model.train()
@@ -275,11 +365,17 @@ class TrainStep:
         for p in self.active:
             p.grad = None
         loss = self._loss()
+        early = self._early if self.flat_adam else None
+        if early is not None:
+            early.arm()
         loss.backward()
         if self.flat_adam:
             for g in self.groups:
-                g.gather_grads_()
-                _all_reduce_mean_(g.flat.grad, self.world, self.pg)
+                if early is not None and g is early.g:
+                    early.finish()                  # first bucket was reduced on the forked stream during backward
+                else:
+                    g.gather_grads_()
+                    _all_reduce_mean_(g.flat.grad, self.world, self.pg)
                 g.publish_grads_()
         elif self.bucket is not None:
             self.bucket.reduce_()

@@ -113,6 +113,69 @@ def _worker_flat(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _worker_early(rank, world, port, q):
+    """train_step.EarlyBucket: the first bucket (gradient-arrival prefix) is reduced from inside backward by the arrival hooks, the
+    remainder after it; the result must equal a per-parameter Adam fed the rank-averaged gradients, and the hook really fires."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import copy
+        from medt_b200.train_step import EarlyBucket, FlatGroup
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(4, 8, 3, padding=1),
+                                  torch.nn.ReLU(), torch.nn.Conv2d(8, 2, 1))
+        ref = copy.deepcopy(net)
+        # arrival order = reverse of the forward order (the head's gradients come first)
+        arrival = [p for m in reversed(list(net)) for p in m.parameters()]
+        group = FlatGroup(arrival)
+        eb = EarlyBucket(group, world, None, frac=0.5)
+        assert 0 < eb.k < len(group.params) and eb.n_early == sum(p.numel() for p in group.params[:eb.k])
+        opt = torch.optim.Adam([group.flat], lr=1e-2, weight_decay=1e-5)
+        opt_ref = torch.optim.Adam(ref.parameters(), lr=1e-2, weight_decay=1e-5)
+        for it in range(3):
+            torch.manual_seed(100 + 10 * it + rank)            # different data shard per rank
+            x, y = torch.rand(4, 3, 8, 8), torch.randint(0, 2, (4, 8, 8))
+            for p in net.parameters():
+                p.grad = None
+            eb.arm()
+            torch.nn.functional.cross_entropy(net(x), y).backward()
+            assert eb.fired                                    # the prefix was reduced from inside backward
+            eb.finish()
+            group.publish_grads_()
+            opt.step()
+            opt_ref.zero_grad(set_to_none=True)
+            torch.nn.functional.cross_entropy(ref(x), y).backward()
+            for p in ref.parameters():
+                dist.all_reduce(p.grad)
+                p.grad.div_(world)
+            opt_ref.step()
+            for a, b in zip(net.parameters(), ref.parameters()):
+                assert torch.allclose(a.detach(), b.detach(), atol=1e-7, rtol=1e-6), it
+        flat = group.flat.detach().clone()
+        both = [torch.zeros_like(flat) for _ in range(world)]
+        dist.all_gather(both, flat)
+        assert torch.equal(both[0], both[1])                   # replicas stay in lock-step
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q.put((rank, repr(e) + traceback.format_exc()[-600:]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_early_bucket_overlapped_allreduce_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_early, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
 def test_flat_group_allreduce_adam_world2_gloo():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
