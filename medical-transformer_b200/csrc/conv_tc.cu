@@ -608,7 +608,7 @@ int tc3_launch(TcConv a, const float* img, const float* w, float* out, cudaStrea
   if (stage_bytes(bn) > 220 * 1024) return 0;
   const long gx = (prow + 127) / 128;
   const int gy = (a.Crow + bn - 1) / bn;
-  long ks = ((long)nsm + gx * gy - 1) / (gx * gy);
+  long ks = (long)nsm / (gx * gy);                                 // one CTA per SM (registers): stay inside ONE wave
   const long ks_max = (nst + 1) / 2;                               // at least two stages per slice
   if (ks > ks_max) ks = ks_max;
   if (ks < 1) ks = 1;
