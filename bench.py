@@ -497,8 +497,10 @@ def run_product(args, rank, world, local_rank):
             r5 = op_profile(dev, flush, "gated", 16, BS, 256, 256, 0, 1, reps=5)
             line["roofline"]["L256_op"] = {"op": f"512-px layer1.0 hight_block C16 L256 B{r5['B']}",
                                            "fwd": op_roofline(r5, pk, "fwd"), "bwd": op_roofline(r5, pk, "bwd")}
+        # the tensor-core kernel of the step (csrc/conv_tc.cu, tcgen05 kind::tf32, 3xTF32 operand split), measured live
+        line["roofline"]["tensor_core_kernel"] = conv_tc_profile(dev, flush, pk)
     except Exception as e:  # noqa: BLE001
-        line["roofline"] = {"error": repr(e)}
+        line["roofline"] = dict(line.get("roofline") or {}, error=repr(e))
     # ---- CPU baseline: the reference's path (oracle port) on this box's host cores, bounded sample
     log("cpu baseline, cores", os.cpu_count())
     if world == 1 and not args.no_cpu_baseline:
@@ -517,6 +519,41 @@ def run_product(args, rank, world, local_rank):
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"]["same_gpu_eager"] = {"error": repr(e)[:200]}
     print(json.dumps(line), flush=True)
+
+
+def conv_tc_profile(dev, flush, pk, reps=10):
+    """k_conv_tc3 through the C ABI (mt_conv2d_forward) on the stem's conv2 (8 -> 128 channels) at the 128-px step's 64 x 64 maps
+    and at the 512-px step's 256 x 256 maps: CUDA events on the launching stream, L2 flushed before every launch.  A 3xTF32 product
+    costs three kind::tf32 MMAs, so the tensor-pipe roof for fp32-grade flops is (dense TF32 peak = measured bf16 peak / 2) / 3."""
+    from medt_b200 import _cabi
+    lib = _cabi.load_library()
+    st = torch.cuda.current_stream(dev).cuda_stream
+    out = {"kernel": "k_conv_tc3<128> (3x3 conv forward: zero-padded slab, 27 tcgen05.mma per 8-channel stage, TMEM accumulators)",
+           "fp32_grade_tensor_roof_TFLOPs": pk["bf16_tflops"] / 2 / 3,
+           "ncu": "profiles/r3_conv_tc3_ncu_full.md (sm__pipe_tensor_cycles_active 12 - 14 % at BN = 128)"}
+    for tag, h in (("conv2_64x64", 64), ("conv2_256x256", 256)):
+        n, ci, co = BS, 8, 128
+        x = torch.randn(n, ci, h, h, device=dev)
+        w = torch.randn(co, ci, 3, 3, device=dev)
+        y = torch.empty(n, co, h, h, device=dev)
+        call = lambda: lib.mt_conv2d_forward(n, ci, co, h, h, 3, 3, 1, 1, x.data_ptr(), w.data_ptr(), y.data_ptr(), st)  # noqa: E731
+        assert call() == 0
+        torch.cuda.synchronize(dev)
+        us = []
+        for _ in range(reps):
+            flush()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            call()
+            b.record()
+            torch.cuda.synchronize(dev)
+            us.append(a.elapsed_time(b) * 1e3)
+        t = sorted(us)[len(us) // 2]
+        flops = 2.0 * n * h * h * co * ci * 9
+        byts = 4.0 * (x.numel() + y.numel() + w.numel())
+        out[tag] = {"us_per_launch_cold_l2": t, "fp32_grade_TFLOPs": flops / t / 1e6, "tensor_frac": flops / t / 1e6 / out["fp32_grade_tensor_roof_TFLOPs"],
+                    "alg_bytes_per_launch": byts, "achieved_GBps": byts / t / 1e3, "hbm_frac": byts / t / 1e3 / pk["hbm_gbs"]}
+    return out
 
 
 def reference_eager_gpu(model_name, dev, steps=10, warmup=3):
