@@ -165,7 +165,7 @@ int mt_conv2d_backward(int N, int Ci, int Co, int H, int W, int KH, int KW, int 
 /* Routing of mt_conv2d_*: 1 (default; env MT_CONV_TC) = the tcgen05 tensor-core kernels (csrc/conv_tc.cu: kind::tf32 MMAs with the
  * 3xTF32 operand split, fp32-grade results, accumulators in TMEM) wherever the shape is eligible, 0 = the FMA-pipe kernels only.
  * Process-wide; not thread-safe against concurrent mt_conv2d_* calls. */
-void mt_set_conv_tc(int mode);
+int mt_set_conv_tc(int mode);     /* returns MT_OK */
 
 /* The tail of a training step: logits = adjust(relu(x)) (1x1 conv with bias to TWO classes, axialnet.py:440,502 / :588,708) fused
  * with loss = F.cross_entropy(logits, y) (metrics.py:17-20, train.py:156; mean over all pixels, labels in {0, 1}).

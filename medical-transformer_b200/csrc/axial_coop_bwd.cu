@@ -1221,10 +1221,12 @@ static int coop_launch_bwd(const Dims& m, const MtAxialParams& p, const MtAxialG
                            const double* stats, const float* coef, const float* yraw, const float* oraw, const float* lse,
                            double* bstats, float* bcoef, unsigned* bcnt, float* dyh, cudaStream_t st) {
   auto kern = k_axial_bwd<D, POS, RT, FUSED>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};          // per device: function attributes live in a context (nn.DataParallel: one process, two GPUs)
+  int adev = 0;
+  if (cudaGetDevice(&adev) != cudaSuccess || adev < 0 || adev >= 64) return -1;
+  if (!attr_set[adev]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess) return -1;
-    attr_set = true;
+    attr_set[adev] = true;
   }
   const int nsm = coop_sm_count();
   const int cap = coop_max_ctas_env();

@@ -781,10 +781,12 @@ template <int D, bool POS, int RT>
 static int coop_launch_fwd(const Dims& m, const MtAxialParams& p, const float* x, float* out, double* stats, float* coef,
                            unsigned* cnt, float* yraw, float* oraw, float* lse, float* tabg, cudaStream_t st) {
   auto kern = k_axial_fwd<D, POS, RT>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};          // per device: function attributes live in a context (nn.DataParallel: one process, two GPUs)
+  int adev = 0;
+  if (cudaGetDevice(&adev) != cudaSuccess || adev < 0 || adev >= 64) return -1;
+  if (!attr_set[adev]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
-    attr_set = true;
+    attr_set[adev] = true;
   }
   const int nsm = coop_sm_count();
   const int cap = coop_max_ctas_env();

@@ -224,7 +224,7 @@ static TcConv cg_tc_geom(const CgArgs& a) {
 
 extern "C" {
 
-void mt_set_conv_tc(int mode) { tc_conv_set_mode(mode); }
+int mt_set_conv_tc(int mode) { tc_conv_set_mode(mode); return MT_OK; }
 
 int mt_conv2d_forward(int N, int Ci, int Co, int H, int W, int KH, int KW, int stride, int pad, const float* x, const float* w,
                       float* y, void* stream) {

@@ -532,10 +532,13 @@ k_conv_tc3(const TcConv a, const float* __restrict__ img, const float* __restric
 
 template <int BN>
 int tc3_launch_bn(const TcConv& a, dim3 grid, int smem, const float* img, const float* w, float* out, cudaStream_t st) {
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
+  static int attr_smem[64] = {};                                   // per device: function attributes belong to a context
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 0;
+  if (smem > attr_smem[dev]) {
     if (cudaFuncSetAttribute(k_conv_tc3<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
-    attr_smem = smem;
+    attr_smem[dev] = smem;
   }
   k_conv_tc3<BN><<<grid, 288, smem, st>>>(a, img, w, out);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
@@ -546,10 +549,13 @@ int g_tc_mode = -1;
 template <int MODE, int BN>
 int tc_launch_bn(const TcConv& a, dim3 grid, const float* img, const float* mat, float* out, cudaStream_t st) {
   constexpr int smem = TC_STAGES * (2 * TC_A_BYTES + 2 * BN * TC_KB * 4);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static int attr_smem[64] = {};                                   // per device: function attributes belong to a context
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 0;
+  if (smem > attr_smem[dev]) {
     if (cudaFuncSetAttribute(k_conv_tc<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
-    attr_done = true;
+    attr_smem[dev] = smem;
   }
   k_conv_tc<MODE, BN><<<grid, 256, smem, st>>>(a, img, mat, out);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;

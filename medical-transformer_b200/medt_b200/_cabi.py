@@ -104,7 +104,7 @@ def load_library():
         lib.mt_conv2d_forward.argtypes = [I, I, I, I, I, I, I, I, I, VP, VP, VP, VP]
         lib.mt_conv2d_backward.restype = C.c_int
         lib.mt_conv2d_backward.argtypes = [I, I, I, I, I, I, I, I, I, VP, VP, VP, VP, VP, VP]
-        lib.mt_set_conv_tc.restype = None
+        lib.mt_set_conv_tc.restype = C.c_int
         lib.mt_set_conv_tc.argtypes = [I]
         lib.mt_head_ce_forward.restype = C.c_int
         lib.mt_head_ce_forward.argtypes = [I, I, I, VP, VP, VP, VP, VP, VP, VP]

@@ -166,6 +166,32 @@ def _conv2d_case(Conv2dGemm, n, ci, co, h, k, stride, pad, bias):
             assert rel(a, b) < 2e-5            # dW sums up to 262 k positions in split slices (fp32 atomics)
 
 
+@pytest.mark.parametrize("n,ci,co,h,k,stride,pad", [(4, 3, 8, 128, 7, 2, 3),       # the 7x7 stem geometry (generic tcgen05 kernel)
+                                                    (1, 5, 20, 12, 3, 1, 1),        # Ci % 8 != 0, ragged sizes: generic kernel, FMA dW
+                                                    (2, 7, 130, 20, 5, 1, 2),       # two output-channel tiles, 5x5
+                                                    (3, 24, 40, 10, 3, 1, 1),       # slab kernel, tiles across image boundaries
+                                                    (2, 8, 16, 130, 3, 1, 1),       # slab kernel, one stage (single smem buffer)
+                                                    (1, 16, 128, 256, 3, 1, 1)])    # slab kernel, W = 256: 64-channel tiles (smem)
+def test_conv2d_tensor_core_kernels_vs_fp64(n, ci, co, h, k, stride, pad):
+    """csrc/conv_tc.cu (tcgen05 kind::tf32, 3xTF32 split, round-robin TMEM accumulators) against torch's fp64 convolution: forward,
+    dX (stride 1) and dW stay at fp32-grade accuracy (< 2e-6; measured 1e-7 .. 5e-7, profiles/r3_conv_tc_accuracy_*.json) on
+    shapes that exercise the generic gathered kernel, the slab kernel's image-boundary tiles and its single-buffer mode."""
+    from medt_b200 import _cabi
+    from medt_b200.shell_ops import Conv2dGemm
+    _cabi.load_library().mt_set_conv_tc(1)
+    torch.manual_seed(11)
+    w = (torch.randn(co, ci, k, k, device="cuda") / (ci * k * k) ** 0.5).requires_grad_(True)
+    x = torch.randn(n, ci, h, h, device="cuda", requires_grad=True)
+    ref = F.conv2d(x.double(), w.double(), stride=stride, padding=pad)
+    d = torch.randn_like(ref)
+    gr = torch.autograd.grad(ref, [x, w], d)
+    got = Conv2dGemm.apply(x, w, stride, pad, 1)
+    gg = torch.autograd.grad(got, [x, w], d.float())
+    rel = lambda a, b: ((a.double() - b).norm() / b.norm()).item()  # noqa: E731
+    assert rel(got, ref) < 2e-6
+    assert rel(gg[0], gr[0]) < 2e-6 and rel(gg[1], gr[1]) < 2e-6
+
+
 @pytest.mark.parametrize("n,c,hw", [(4, 16, 128), (2, 16, 256), (3, 8, 33)])
 def test_head_ce_matches_torch(n, c, hw):
     """medt_b200.shell_ops.head_ce == F.cross_entropy(adjust(F.relu(x)), y): loss, logits and every gradient"""
