@@ -13,6 +13,7 @@
 // so a CTA always serves the same head group and stages its slice of W_qkv once.
 #pragma once
 #include "axial_attn2.cuh"
+#include "pdl.cuh"
 
 #define MT_COOP_THREADS 256
 
@@ -27,7 +28,7 @@ static inline DivS make_divs(int d) {
 }
 // (the general case is a real call: inlined, every division site carries ~30 cold instructions, and instruction fetch is the
 //  top stall of these run-once kernels -- ncu: stalled_no_instruction 31 % of warp time)
-__device__ __forceinline__ int slow_div(int x, int d) { return x / d; }
+static __device__ __noinline__ int slow_div(int x, int d) { return x / d; }
 __device__ __forceinline__ int dv(int x, const DivS k) { return k.lg >= 0 ? (x >> k.lg) : slow_div(x, k.d); }
 __device__ __forceinline__ int md(int x, const DivS k) { return k.lg >= 0 ? (x & (k.d - 1)) : x - slow_div(x, k.d) * k.d; }
 

@@ -986,6 +986,7 @@ k_axial_bwd(Dims m, MtAxialParams p, MtAxialGrads gr, CoopPlanB pl, const float*
   }
   phase_stamp(m, 5);
   grid_barrier(bar, G, epoch);
+  pdl_launch_dependents();          // last phase: a PDL-launched successor (pdl.cuh) may take its SM slots now and wait there
   phase_stamp(m, 6);
 
   // ================================================================== B4: bn_qkv backward + dX = W^T dy_raw

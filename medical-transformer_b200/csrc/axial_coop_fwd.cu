@@ -587,6 +587,7 @@ k_axial_fwd(Dims m, MtAxialParams p, CoopPlan pl, const float* __restrict__ x, f
   }
   phase_stamp(m, 6);
   if (train) grid_barrier(bar, G, epoch);
+  pdl_launch_dependents();          // last phase: a PDL-launched successor (pdl.cuh) may take its SM slots now and wait there
   phase_stamp(m, 7);
 
   // =================================================================================== P4: bn_output + un-permute (+ pool)

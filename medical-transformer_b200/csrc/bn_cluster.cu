@@ -7,6 +7,7 @@
 // sums added in rank order (deterministic).  Slices too large for the registers (512-px inputs) are re-read, still CS-fold wider.
 #include "common.cuh"
 #include "bn_cluster.cuh"
+#include "pdl.cuh"
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
@@ -55,6 +56,7 @@ __global__ void __launch_bounds__(256)
 k_bn_act_fwd_cl(BnActArgs a, int CS, const float4* __restrict__ x, const float4* __restrict__ res, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float* __restrict__ rm, float* __restrict__ rv, float4* __restrict__ y,
                 float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  pdl_entry();
   cg::cluster_group cl = cg::this_cluster();
   const int rank = (int)cl.block_rank();
   const int c = blockIdx.x / CS, g = blockIdx.y, tid = threadIdx.x;
@@ -136,6 +138,7 @@ __global__ void __launch_bounds__(256)
 k_bn_act_bwd_cl(BnActArgs a, int CS, const float4* __restrict__ x, const float4* __restrict__ y, const float4* __restrict__ dy,
                 const float* __restrict__ gamma, const float* __restrict__ save_mean, const float* __restrict__ save_invstd,
                 float4* __restrict__ dx, float4* __restrict__ dres, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_entry();
   cg::cluster_group cl = cg::this_cluster();
   const int rank = (int)cl.block_rank();
   const int c = blockIdx.x / CS, g = blockIdx.y, tid = threadIdx.x;
@@ -210,16 +213,7 @@ void bc_plan(const BnActArgs& a, int& cs, bool& hold) {
 
 template <typename K, typename... Args>
 int bc_launch(K kern, const BnActArgs& a, int cs, cudaStream_t st, Args... args) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(a.C * cs), (unsigned)a.G, 1);
-  cfg.blockDim = dim3(256, 1, 1);
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, args...) == cudaSuccess ? 1 : -1;
+  return mt_launch_pdl(kern, dim3((unsigned)(a.C * cs), (unsigned)a.G, 1), dim3(256, 1, 1), 0, st, cs, args...) == cudaSuccess ? 1 : -1;
 }
 
 }  // namespace

@@ -177,14 +177,20 @@ __device__ __forceinline__ BnBwdCoef bn_bwd_coef(int training, double sum, doubl
 __device__ __forceinline__ double* stat_slot(const Dims& m, double* base, int grp, int nstat, int cta) {
   return base + ((size_t)(cta & (m.nrep - 1)) * m.ngroups + grp) * nstat;
 }
-__device__ __forceinline__ double stat_get(const Dims& m, const double* base, int grp, int nstat, int off) {
-  if (m.nrep == 1) return __ldcg(base + (size_t)grp * nstat + off);
+// ONE out-of-line copy: inlined, each of the ~40 call sites of a cooperative kernel carried ~100 SASS lines (8 address
+// computations, 8 loads, 7 fp64 adds) -- 25 % of a 260 KB kernel whose warps execute almost every instruction exactly once, so
+// that instruction fetch is its top stall (ncu: stall_no_inst 41 % of the samples of k_axial_fwd<4,1,2>, profiles/r3_notes.md)
+static __device__ __noinline__ double stat_get_rep(const double* p, size_t rep_stride) {
   double v[MT_NREP], s = 0.0;
 #pragma unroll
-  for (int r = 0; r < MT_NREP; ++r) v[r] = __ldcg(base + ((size_t)r * m.ngroups + grp) * nstat + off);   // 8 loads in flight
+  for (int r = 0; r < MT_NREP; ++r) v[r] = __ldcg(p + (size_t)r * rep_stride);   // 8 loads in flight
 #pragma unroll
   for (int r = 0; r < MT_NREP; ++r) s += v[r];
   return s;
+}
+__device__ __forceinline__ double stat_get(const Dims& m, const double* base, int grp, int nstat, int off) {
+  if (m.nrep == 1) return __ldcg(base + (size_t)grp * nstat + off);
+  return stat_get_rep(base + (size_t)grp * nstat + off, (size_t)m.ngroups * nstat);
 }
 
 // sequential EMA of the running statistics over the statistic groups (one BN call each)

@@ -8,6 +8,7 @@
 // cuDNN's fp32 (non-TF32) kernels for these shapes take 17-29 us each (profiles/r1_notes.md); TF32 is not
 // an option.
 #include "common.cuh"
+#include "pdl.cuh"
 extern thread_local cudaError_t g_last_cuda;
 int mt_fail_msg(int code, const char* msg);
 cudaStream_t mt_side_fork(cudaStream_t main_stream);
@@ -45,6 +46,7 @@ __device__ __forceinline__ bool c1_pos(const C1Args& a, long q, int& n, int& src
 // grid (ceil(P/64), ceil(Co/64)); M = co, N = positions
 __global__ void __launch_bounds__(256)
 k_c1_fwd(C1Args a, const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y) {
+  pdl_entry();
   __shared__ __align__(16) float As[16 * C1_LD], Bs[16 * C1_LD];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int co0 = blockIdx.y * 64;
@@ -99,6 +101,7 @@ k_c1_fwd(C1Args a, const float* __restrict__ x, const float* __restrict__ w, flo
 __global__ void __launch_bounds__(256)
 k_c1_dx(C1Args a, const float* __restrict__ dy, const float* __restrict__ w, const float* __restrict__ x,
         float* __restrict__ dx) {
+  pdl_entry();
   __shared__ __align__(16) float As[16 * C1_LD], Bs[16 * C1_LD];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int ci0 = blockIdx.y * 64;
@@ -202,6 +205,12 @@ int mt_conv1x1_forward(int N, int Ci, int Co, int H, int W, int stride, int relu
     return mt_fail_msg(MT_ERR_BAD_ARG, "mt_conv1x1_forward: bad argument");
   C1Args a{N, Ci, Co, H, W, stride, (H - 1) / stride + 1, (W - 1) / stride + 1, relu_in ? 1 : 0};
   const long P = (long)N * a.Ho * a.Wo;
+#if defined(__CUDACC__)
+  if (mt_pdl_enabled()) {
+    if (mt_launch_pdl(k_c1_fwd, dim3((unsigned)((P + 63) / 64), (Co + 63) / 64), dim3(256), 0, (cudaStream_t)stream, 1, a, x, w, y) != cudaSuccess)
+      return mt_fail_msg(MT_ERR_CUDA, "mt_conv1x1_forward: launch failed");
+  } else
+#endif
   k_c1_fwd<<<dim3((unsigned)((P + 63) / 64), (Co + 63) / 64), 256, 0, (cudaStream_t)stream>>>(a, x, w, y);
   g_last_cuda = cudaGetLastError();
   return g_last_cuda == cudaSuccess ? MT_OK : mt_fail_msg(MT_ERR_CUDA, "mt_conv1x1_forward: launch failed");
@@ -227,6 +236,10 @@ int mt_conv1x1_backward(int N, int Ci, int Co, int H, int W, int stride, int rel
   }
   if (dx) {
     if (stride > 1) cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)N * Ci * H * W, st);
+#if defined(__CUDACC__)
+    if (mt_pdl_enabled()) mt_launch_pdl(k_c1_dx, dim3((unsigned)((P + 63) / 64), (Ci + 63) / 64), dim3(256), 0, st, 1, a, dy, w, x, dx);
+    else
+#endif
     k_c1_dx<<<dim3((unsigned)((P + 63) / 64), (Ci + 63) / 64), 256, 0, st>>>(a, dy, w, x, dx);
   }
   mt_side_join(st, sd);

@@ -19,6 +19,7 @@
 //     Split-K slices accumulate with fp32 atomics into the zeroed output (last-bit run-to-run differences, as in conv_gemm.cu).
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "pdl.cuh"
 #include <cstdlib>
 
 namespace {
@@ -340,6 +341,7 @@ k_conv_tc(const TcConv a, const float* __restrict__ img, const float* __restrict
 template <int BN>
 __global__ void __launch_bounds__(288, 1)
 k_conv_tc3(const TcConv a, const float* __restrict__ img, const float* __restrict__ wgt, float* __restrict__ out) {
+  pdl_entry();
   constexpr int NACC = tc_nacc(BN);                           // independent TMEM accumulators, summed in fp32 by the epilogue
   constexpr uint32_t TMEM_COLS = NACC * BN;
   constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -540,6 +542,7 @@ int tc3_launch_bn(const TcConv& a, dim3 grid, int smem, const float* img, const 
     if (cudaFuncSetAttribute(k_conv_tc3<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
     attr_smem[dev] = smem;
   }
+  if (mt_pdl_enabled()) return mt_launch_pdl(k_conv_tc3<BN>, grid, dim3(288), (size_t)smem, st, 1, a, img, w, out) == cudaSuccess ? 1 : -1;
   k_conv_tc3<BN><<<grid, 288, smem, st>>>(a, img, w, out);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

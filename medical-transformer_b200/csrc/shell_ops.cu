@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include "common.cuh"
 #include "bn_cluster.cuh"
+#include "pdl.cuh"
 #include <cstdlib>
 
 // ---------------------------------------------------------------------------------------------
@@ -27,6 +28,7 @@ __device__ __forceinline__ void up_taps(int dst, int n_in, int& i0, int& i1, flo
 __global__ void __launch_bounds__(256)
 k_up2x_fwd(int planes, int C, int H, int W, const float* __restrict__ in, const float* __restrict__ bias,
            const float* __restrict__ skip, float* __restrict__ out, unsigned char* __restrict__ mask) {
+  pdl_entry();
   const int Wo = 2 * W, Ho = 2 * H;
   const long total = (long)planes * Ho * W;                 // W pairs per output row
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -63,6 +65,7 @@ k_up2x_fwd(int planes, int C, int H, int W, const float* __restrict__ in, const 
 __global__ void __launch_bounds__(256)
 k_up2x_bwd(int planes, int C, int H, int W, const float* __restrict__ dout, const unsigned char* __restrict__ mask,
            float* __restrict__ din, float* __restrict__ dbias) {
+  pdl_entry();
   const long total = (long)planes * H * W;
   const long gidx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool act = gidx < total;
@@ -361,6 +364,10 @@ int mt_up2x_relu_add_forward(int planes, int C, int H, int W, const float* in, c
     return mt_fail_msg(MT_ERR_BAD_ARG, "mt_up2x_relu_add_forward: bad argument");
   if (!mt_al16(out) || !mt_al16(skip)) return mt_fail_msg(MT_ERR_BAD_ARG, "mt_up2x_relu_add_forward: out / skip must be 16-byte aligned");
   const long total = (long)planes * 2 * H * W;
+#if defined(__CUDACC__)
+  if (mt_pdl_enabled()) mt_launch_pdl(k_up2x_fwd, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 1, planes, C, H, W, in, bias, skip, out, mask);
+  else
+#endif
   k_up2x_fwd<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(planes, C, H, W, in, bias, skip, out, mask);
   g_last_cuda = cudaGetLastError();
   return g_last_cuda == cudaSuccess ? MT_OK : mt_fail_msg(MT_ERR_CUDA, "mt_up2x_relu_add_forward: launch failed");
