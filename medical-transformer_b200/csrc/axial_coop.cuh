@@ -19,18 +19,21 @@
 
 template <> struct VecT<1> { typedef float T; };
 
-// divisor known on the host: shift when it is a power of two (every reference shape), plain division otherwise
-struct DivS { int d, lg; };
+// divisor known on the host: x / d as ONE multiply-high, branch free:  q = umulhi(x, mul) + (x & one)
+//   d = 1: mul = 0, one = ~0;   d = 2^k: mul = 2^(32-k) (exact for every x);   else mul = floor(2^32 / d) + 1, exact while x * d < 2^32
+// (x is an index into a shared-memory slot or a unit count: < 2^18, d <= L * rows <= 2^12).  The earlier form -- shift when d is a
+// power of two, else a division -- cost a compare, a branch and a call sequence at each of the ~80 sites of a cooperative kernel: 6 %
+// of the code of kernels whose top stall is instruction fetch.
+struct DivS { int d, lg; unsigned mul, one; };
 static inline DivS make_divs(int d) {
   DivS k; k.d = d > 0 ? d : 1; k.lg = -1;
   for (int b = 0; b < 31; ++b) if ((1 << b) == k.d) k.lg = b;
+  if (k.d == 1) { k.mul = 0u; k.one = 0xffffffffu; }
+  else { k.mul = (unsigned)((1ull << 32) / (unsigned)k.d) + (k.lg >= 0 ? 0u : 1u); k.one = 0u; }
   return k;
 }
-// (the general case is a real call: inlined, every division site carries ~30 cold instructions, and instruction fetch is the
-//  top stall of these run-once kernels -- ncu: stalled_no_instruction 31 % of warp time)
-static __device__ __noinline__ int slow_div(int x, int d) { return x / d; }
-__device__ __forceinline__ int dv(int x, const DivS k) { return k.lg >= 0 ? (x >> k.lg) : slow_div(x, k.d); }
-__device__ __forceinline__ int md(int x, const DivS k) { return k.lg >= 0 ? (x & (k.d - 1)) : x - slow_div(x, k.d) * k.d; }
+__device__ __forceinline__ int dv(int x, const DivS k) { return (int)(__umulhi((unsigned)x, k.mul) + ((unsigned)x & k.one)); }
+__device__ __forceinline__ int md(int x, const DivS k) { return x - dv(x, k) * k.d; }
 
 // BN coefficients of one channel straight from the fp64 accumulators (training) or the running statistics (eval): ONE
 // out-of-line copy shared by every phase of the cooperative kernels
