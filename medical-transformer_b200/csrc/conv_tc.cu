@@ -7,7 +7,10 @@
 // split into hi = rn_tf32(x) and lo = rn_tf32(x - hi); D += A_hi.B_lo + A_lo.B_hi + A_hi.B_hi drops only the lo.lo term
 // (<= 2^-22 relative per product), i.e. fp32-grade products on the tensor pipe at 1/3 of its TF32 rate.
 //
-// One CTA = one 128 x BN tile of D and one slice of the reduction:
+// Two kernels: the GENERIC one described next (any K x K / stride; used for decoder1's strided forward and odd shapes) and the
+// 3x3 / stride-1 SLAB kernel further down (k_conv_tc3: every other stem / decoder convolution, forward and dX) -- see its header.
+//
+// Generic kernel: one CTA = one 128 x BN tile of D and one slice of the reduction:
 //   * 256 threads.  Warps 0-3: one A row each (128 rows), warps 4-7: the BN rows of B.  Per k block of 32 they gather their
 //     elements straight from the NCHW tensors (im2col is never materialised; zero padding and tails are predicated), split them
 //     into hi / lo and store them as the UMMA canonical K-major SWIZZLE_NONE layout (core matrix = 8 rows x 16 B, chunk-major:

@@ -17,8 +17,8 @@ struct TcConv {
   int R, tiles_per_img, nbuf;                                       // slab kernel (3x3 / stride 1): slab rows, tiles per image, smem buffers
 };
 
-// 1 = launched, 0 = shape not eligible (caller uses the FMA kernels), < 0 = CUDA error.  `out` must be zeroed by the caller when the
-// launcher reports atomic accumulation through *needs_zero (it does the memset itself on `st`).
+// 1 = launched, 0 = shape not eligible (caller uses the FMA kernels), < 0 = CUDA error.  When the launcher splits the reduction over
+// gridDim.z it zeroes `out` itself (cudaMemsetAsync on `st`) and the slices accumulate with fp32 atomics.
 int tc_conv_fwd_or_dgrad(const TcConv& geom, const float* img, const float* w, float* out, cudaStream_t st);
 int tc_conv_wgrad(const TcConv& geom, const float* x, const float* dy, float* dw, cudaStream_t st);
 int tc_conv_mode();              // MT_CONV_TC / mt_set_conv_tc: 0 off, 1 on (default), 2 on + debug bit 0
