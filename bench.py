@@ -490,7 +490,9 @@ def run_product(args, rank, world, local_rank):
                             "peak_source": f"MEASURED_PEAKS.json ({pk_kind})", "traffic": tr,
                             "alg_bytes_per_launch": rb["alg_bytes_per_launch"], "us_per_launch_cold_l2": rb["us_per_launch_cold_l2"],
                             "us_per_launch_warm_l2": rb["us_per_launch_warm_l2"],
-                            "fractions_of_each_roof": fr, "binding": max(fr, key=fr.get) + " (issue/latency-bound: no roof is reached at 128 px, SURVEY 8(d))",
+                            "fractions_of_each_roof": fr, "binding": max(fr, key=fr.get) + " is the nearest roof, but none is reached at 128 px (SURVEY 8(d)): the kernel is "
+                                       "instruction-fetch / latency-bound (ncu: stall_no_inst + barrier = 67 % of the warp samples on the small "
+                                       "layers, DESIGN.md 5d); `bound` names the memory roof only because the contract allows hbm | tensor",
                             "forward_kernel": dict(kernel="k_axial_fwd<2,true,2>", **rf)}
         if args.configs and SZ == 128 and "512" in args.configs:
             # BASELINE config 5 geometry (L = 256): the exp roof binds there
